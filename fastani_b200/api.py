@@ -1,0 +1,357 @@
+"""ctypes host side of libfastani_b200.so, mirroring the reference's seam for the hot path:
+
+    skch::Parameters  -> Parameters        (src/map/include/map_parameters.hpp:22-41)
+    skch::Sketch      -> Sketch            (src/map/include/winSketch.hpp:44-115)
+    skch::Map         -> Map               (src/map/include/computeMap.hpp:35-102)
+    cgi::computeCGI   -> compute_cgi       (src/cgi/include/computeCoreIdentity.hpp:166-298)
+
+Same names and argument meaning; errors surface as BaniError (the reference exit(1)s earlier,
+in validateInputFiles).  No CPU fallback: a missing library or GPU raises.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "lib", "libfastani_b200.so")
+_LIB = None
+
+MAPPING_DTYPE = np.dtype([
+    ("queryLen", "<i4"), ("refStartPos", "<i4"), ("refEndPos", "<i4"),
+    ("queryStartPos", "<i4"), ("queryEndPos", "<i4"), ("refSeqId", "<i4"),
+    ("querySeqId", "<i4"), ("nucIdentity", "<f4"), ("nucIdentityUpperBound", "<f4"),
+    ("sketchSize", "<i4"), ("conservedSketches", "<i4")])
+MINIMIZER_DTYPE = np.dtype([("hash", "<u4"), ("seqId", "<i4"), ("wpos", "<i4")])
+CGI_DTYPE = np.dtype([("refGenomeId", "<i4"), ("qryGenomeId", "<i4"), ("countSeq", "<i4"),
+                      ("totalQueryFragments", "<i4"), ("identity", "<f4")])
+
+
+class BaniError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("fastani_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class _Params(C.Structure):
+    _fields_ = [("kmer_size", C.c_int32), ("window_size", C.c_int32), ("frag_len", C.c_int32),
+                ("perc_identity", C.c_float), ("p_value", C.c_double), ("reference_size", C.c_uint64),
+                ("reserved", C.c_int32 * 8)]
+
+
+class MapCounters(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("fragments", "sum_s", "hits", "candidates", "n2", "mappings")] + \
+               [("reserved", C.c_uint64 * 4)]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n in ("fragments", "sum_s", "hits", "candidates", "n2", "mappings")}
+
+
+def library_path():
+    return _LIB_PATH
+
+
+def load_library():
+    """Loads the CUDA library.  Raises (never falls back) when it has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(_LIB_PATH):
+        raise BaniError(-2, "%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                            "(there is no CPU fallback)" % _LIB_PATH)
+    L = C.CDLL(_LIB_PATH)
+    vp, i32, i64, u64, u32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_uint32
+    P = C.POINTER
+    sig = {
+        "bani_last_error": (C.c_char_p, []),
+        "bani_version": (C.c_char_p, []),
+        "bani_params_default": (None, [P(_Params)]),
+        "bani_recommended_window_size": (C.c_int, [P(_Params)]),
+        "bani_stat_min_hits_relaxed": (C.c_int, [C.c_int, C.c_int, C.c_float]),
+        "bani_stat_identity": (C.c_int, [C.c_int, C.c_int, C.c_int, P(C.c_float), P(C.c_float)]),
+        "bani_ctx_create": (C.c_int, [C.c_int, P(_Params), P(vp)]),
+        "bani_ctx_destroy": (None, [vp]),
+        "bani_ctx_params": (C.c_int, [vp, P(_Params)]),
+        "bani_ctx_sync": (C.c_int, [vp]),
+        "bani_ctx_stream": (vp, [vp]),
+        "bani_host_alloc": (C.c_int, [C.c_size_t, P(vp)]),
+        "bani_host_free": (None, [vp]),
+        "bani_genome_create": (C.c_int, [vp, i32, vp, vp, P(vp)]),
+        "bani_genome_create_batch": (C.c_int, [vp, i32, vp, vp, vp, P(vp)]),
+        "bani_genome_destroy": (None, [vp]),
+        "bani_genome_info": (C.c_int, [vp, P(i32), P(u64), P(u64), P(u64)]),
+        "bani_genome_decode": (C.c_int, [vp, vp, i32, vp, i64]),
+        "bani_index_build": (C.c_int, [vp, P(vp), i32, P(vp)]),
+        "bani_index_destroy": (None, [vp]),
+        "bani_index_stats": (C.c_int, [vp, P(u64), P(u64), P(u64), P(u64), P(u64)]),
+        "bani_index_minimizers": (C.c_int, [vp, vp, vp, u64]),
+        "bani_index_lookup": (C.c_int, [vp, vp, u32, vp, vp, u64, P(u64)]),
+        "bani_map_genome": (C.c_int, [vp, vp, vp, P(vp), P(u64), P(u64), P(MapCounters)]),
+        "bani_map_cgi": (C.c_int, [vp, vp, P(vp), i32, P(vp), P(u64), vp, P(MapCounters)]),
+        "bani_free": (None, [vp]),
+        "bani_synth_genome": (C.c_int, [vp, u64, u32, u32, u32, i64, vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)          # AttributeError if the ABI lost a symbol
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = L
+    return L
+
+
+EXPORTED_SYMBOLS = [
+    "bani_last_error", "bani_version", "bani_params_default", "bani_recommended_window_size",
+    "bani_stat_min_hits_relaxed", "bani_stat_identity", "bani_ctx_create", "bani_ctx_destroy", "bani_ctx_params",
+    "bani_ctx_sync", "bani_ctx_stream", "bani_host_alloc", "bani_host_free", "bani_genome_create",
+    "bani_genome_create_batch", "bani_genome_destroy", "bani_genome_info", "bani_genome_decode", "bani_index_build",
+    "bani_index_destroy", "bani_index_stats", "bani_index_minimizers", "bani_index_lookup", "bani_map_genome",
+    "bani_map_cgi", "bani_free", "bani_synth_genome"]
+
+
+def _check(rc):
+    if rc != 0:
+        raise BaniError(rc, load_library().bani_last_error().decode())
+
+
+class Parameters:
+    """skch::Parameters with the defaults of parseandSave (parseCmdArgs.hpp:118-130)."""
+
+    def __init__(self, kmerSize=16, minReadLength=3000, windowSize=0, percentageIdentity=80.0,
+                 p_value=1e-3, referenceSize=5000000, minFraction=0.2):
+        self.kmerSize = kmerSize
+        self.minReadLength = minReadLength
+        self.windowSize = windowSize
+        self.percentageIdentity = percentageIdentity
+        self.p_value = p_value
+        self.referenceSize = referenceSize
+        self.minFraction = minFraction
+
+    def _c(self):
+        p = _Params()
+        load_library().bani_params_default(C.byref(p))
+        p.kmer_size = self.kmerSize
+        p.window_size = self.windowSize
+        p.frag_len = self.minReadLength
+        p.perc_identity = self.percentageIdentity
+        p.p_value = self.p_value
+        p.reference_size = self.referenceSize
+        return p
+
+    def recommendedWindowSize(self):
+        """Stat::recommendedWindowSize (map_stats.hpp:226-256)."""
+        p = self._c()
+        r = load_library().bani_recommended_window_size(C.byref(p))
+        if r < 0:
+            _check(r)
+        return r
+
+
+class Context:
+    """One per GPU: CUDA stream, scratch pool and statistic tables."""
+
+    def __init__(self, params=None, device=0):
+        self.lib = load_library()
+        self.params = params or Parameters()
+        p = self.params._c()
+        h = C.c_void_p()
+        _check(self.lib.bani_ctx_create(device, C.byref(p), C.byref(h)))
+        self.h = h
+        self.device = device
+        q = _Params()
+        _check(self.lib.bani_ctx_params(self.h, C.byref(q)))
+        self.windowSize = q.window_size
+
+    def sync(self):
+        _check(self.lib.bani_ctx_sync(self.h))
+
+    @property
+    def stream(self):
+        return self.lib.bani_ctx_stream(self.h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.bani_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- genomes
+    def genome(self, contigs):
+        return self.genomes([contigs])[0]
+
+    def genomes(self, list_of_contig_lists, names=None):
+        """list_of_contig_lists[g] = [(name, bytes-like)] or [bytes-like].  One device sync for the batch."""
+        metas, flat = [], []
+        for cl in list_of_contig_lists:
+            m = []
+            for c in cl:
+                nm, sq = c if isinstance(c, tuple) else ("", c)
+                a = np.frombuffer(sq, dtype=np.uint8) if not isinstance(sq, np.ndarray) else sq
+                m.append((nm, len(a)))
+                flat.append(a)
+            metas.append(m)
+        gen_off = np.zeros(len(metas) + 1, np.int32)
+        gen_off[1:] = np.cumsum([len(m) for m in metas])
+        off = np.zeros(len(flat) + 1, np.int64)
+        if flat:
+            off[1:] = np.cumsum([len(a) for a in flat])
+        seq = np.concatenate(flat) if flat else np.zeros(1, np.uint8)
+        return self.genomes_from_buffer(seq, off, gen_off, metas)
+
+    def genomes_from_buffer(self, seq, off, gen_off, metas=None):
+        """seq: one uint8 host buffer (numpy, may be pinned); contig c = seq[off[c]:off[c+1]];
+        genome g owns contigs gen_off[g]:gen_off[g+1]."""
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        gen_off = np.ascontiguousarray(gen_off, dtype=np.int32)
+        n = len(gen_off) - 1
+        hs = (C.c_void_p * max(n, 1))()
+        _check(self.lib.bani_genome_create_batch(self.h, n, gen_off.ctypes.data, off.ctypes.data, seq.ctypes.data, hs))
+        out = []
+        for g in range(n):
+            c0, c1 = int(gen_off[g]), int(gen_off[g + 1])
+            meta = metas[g] if metas is not None else [("", int(off[c + 1] - off[c])) for c in range(c0, c1)]
+            out.append(Genome(self, C.c_void_p(hs[g]), meta))
+        return out
+
+    def pinned(self, nbytes):
+        """A pinned uint8 host buffer (numpy view); freed when the returned array's base is collected."""
+        p = C.c_void_p()
+        _check(self.lib.bani_host_alloc(nbytes, C.byref(p)))
+        buf = (C.c_uint8 * max(nbytes, 1)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=np.uint8, count=nbytes)
+        _PINNED[p.value] = (self.lib, buf)
+        return arr
+
+    def synth_genome(self, seed, ancestor, strain, ppm, length, out=None):
+        if out is None:
+            out = np.empty(length, np.uint8)
+        _check(self.lib.bani_synth_genome(self.h, seed, ancestor, strain, ppm, length, out.ctypes.data))
+        return out
+
+
+_PINNED = {}
+
+
+class Genome:
+    """A genome resident in HBM (2-bit packed contigs + exception list)."""
+
+    def __init__(self, ctx, handle, meta):
+        self.ctx, self.h, self.metadata = ctx, handle, meta     # metadata: [(name, len)] == ContigInfo
+
+    def info(self):
+        nc, tl, ne, nf = C.c_int32(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        _check(self.ctx.lib.bani_genome_info(self.h, C.byref(nc), C.byref(tl), C.byref(ne), C.byref(nf)))
+        return {"n_contigs": nc.value, "total_len": tl.value, "n_exceptions": ne.value}
+
+    def decode(self, contig):
+        n = self.metadata[contig][1]
+        out = np.empty(max(n, 1), np.uint8)
+        _check(self.ctx.lib.bani_genome_decode(self.ctx.h, self.h, contig, out.ctypes.data, n))
+        return out[:n]
+
+    def close(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            self.ctx.lib.bani_genome_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Sketch:
+    """skch::Sketch: builds the reference index on construction (winSketch.hpp:109-115)."""
+
+    def __init__(self, ctx, ref_genomes):
+        self.ctx = ctx
+        self.refs = list(ref_genomes)
+        arr = (C.c_void_p * max(len(self.refs), 1))(*[g.h for g in self.refs])
+        h = C.c_void_p()
+        _check(ctx.lib.bani_index_build(ctx.h, arr, len(self.refs), C.byref(h)))
+        self.h = h
+        # public members of the reference class
+        self.metadata = [m for g in self.refs for m in g.metadata]                  # winSketch.hpp:66
+        self.sequencesByFileInfo = list(np.cumsum([len(g.metadata) for g in self.refs]).astype(int))   # :75
+
+    def stats(self):
+        a = [C.c_uint64() for _ in range(5)]
+        _check(self.ctx.lib.bani_index_stats(self.h, *[C.byref(x) for x in a]))
+        return dict(zip(("n_minimizers", "n_unique", "total_len", "n_contigs", "n_genomes"), [x.value for x in a]))
+
+    def minimizerIndex(self):
+        """Sketch::minimizerIndex (position order), as a MINIMIZER_DTYPE array."""
+        n = self.stats()["n_minimizers"]
+        out = np.empty(max(n, 1), MINIMIZER_DTYPE)
+        _check(self.ctx.lib.bani_index_minimizers(self.ctx.h, self.h, out.ctypes.data, n))
+        return out[:n]
+
+    def lookup(self, hash_value, cap=1 << 16):
+        """minimizerPosLookupIndex.find(hash) -> [(seqId, wpos)]"""
+        s = np.empty(cap, np.int32); w = np.empty(cap, np.int32); n = C.c_uint64()
+        _check(self.ctx.lib.bani_index_lookup(self.ctx.h, self.h, int(hash_value), s.ctypes.data, w.ctypes.data, cap, C.byref(n)))
+        m = min(n.value, cap)
+        return list(zip(s[:m].tolist(), w[:m].tolist())), n.value
+
+    def sanityCheck(self, maxRatioDiff):
+        """Sketch::sanityCheck (winSketch.hpp:298-318), float32 arithmetic as in the reference."""
+        st = self.stats()
+        if st["n_minimizers"] == 0 or st["n_unique"] == 0:
+            return True, np.float32(0)
+        hashRatio = np.float32(st["total_len"]) / np.float32(st["n_minimizers"])
+        uniqHashRatio = np.float32(st["total_len"]) / np.float32(st["n_unique"])
+        diff = np.float32(abs(hashRatio - uniqHashRatio))
+        return (not diff > np.float32(maxRatioDiff)), diff
+
+    def close(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            self.ctx.lib.bani_index_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Map:
+    """skch::Map: maps one query genome on construction and hands every mapping to `f`
+    (computeMap.hpp:93-102); results also kept in .rows (MAPPING_DTYPE)."""
+
+    def __init__(self, ctx, refSketch, query_genome, f=None):
+        rows = C.c_void_p(); n = C.c_uint64(); tot = C.c_uint64(); ctr = MapCounters()
+        _check(ctx.lib.bani_map_genome(ctx.h, refSketch.h, query_genome.h, C.byref(rows), C.byref(n), C.byref(tot), C.byref(ctr)))
+        if n.value:
+            buf = (C.c_uint8 * (44 * n.value)).from_address(rows.value)
+            self.rows = np.frombuffer(buf, dtype=MAPPING_DTYPE).copy()
+            ctx.lib.bani_free(rows)
+        else:
+            self.rows = np.empty(0, MAPPING_DTYPE)
+        self.totalQueryFragments = tot.value
+        self.counters = ctr
+        if f is not None:
+            for r in self.rows:
+                f(r)
+
+
+def compute_cgi(ctx, refSketch, query_genomes):
+    """Fused map + cgi::computeCGI on the device for a list of query genomes.
+    Returns (results[CGI_DTYPE], totalQueryFragments[len(queries)], MapCounters)."""
+    qs = list(query_genomes)
+    arr = (C.c_void_p * max(len(qs), 1))(*[g.h for g in qs])
+    res = C.c_void_p(); n = C.c_uint64(); ctr = MapCounters()
+    tot = np.zeros(max(len(qs), 1), np.uint64)
+    _check(ctx.lib.bani_map_cgi(ctx.h, refSketch.h, arr, len(qs), C.byref(res), C.byref(n), tot.ctypes.data, C.byref(ctr)))
+    if n.value:
+        buf = (C.c_uint8 * (CGI_DTYPE.itemsize * n.value)).from_address(res.value)
+        out = np.frombuffer(buf, dtype=CGI_DTYPE).copy()
+        ctx.lib.bani_free(res)
+    else:
+        out = np.empty(0, CGI_DTYPE)
+    return out, tot[:len(qs)], ctr

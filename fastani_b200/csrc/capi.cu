@@ -1,0 +1,329 @@
+// capi.cu -- the extern "C" boundary declared in include/fastani_b200.h
+#include "common.cuh"
+#include <cstring>
+#include <cstdlib>
+
+struct bani_ctx    { bani::Ctx c; };
+struct bani_genome { bani::Genome g; };
+struct bani_index  { bani::Index *ix; };
+
+namespace bani {
+static thread_local std::string g_err;
+void set_last_error(const std::string &m) { g_err = m; }
+}
+
+using namespace bani;
+
+#define BANI_TRY try {
+#define BANI_CATCH } catch (const bani::Error &e) { bani::set_last_error(e.what()); return e.code; } \
+  catch (const std::bad_alloc &) { bani::set_last_error("host allocation failed"); return BANI_ERR_NOMEM; } \
+  catch (const std::exception &e) { bani::set_last_error(e.what()); return BANI_ERR_INTERNAL; }
+
+extern "C" {
+
+const char *bani_last_error(void) { return g_err.c_str(); }
+const char *bani_version(void) { return "fastani_b200 0.1 (sm_100a)"; }
+
+void bani_params_default(bani_params *p)
+{
+  // parseandSave defaults, src/map/include/parseCmdArgs.hpp:118-130
+  memset(p, 0, sizeof *p);
+  p->kmer_size = 16; p->window_size = 0; p->frag_len = 3000; p->perc_identity = 80.0f;
+  p->p_value = 1e-3; p->reference_size = 5000000;
+}
+
+int bani_recommended_window_size(const bani_params *p)
+{
+  BANI_TRY
+  if (!p || p->kmer_size < 1 || p->frag_len < 1) fail(BANI_ERR_ARG, "bad parameters");
+  return stat_recommended_window_size(p->p_value, p->kmer_size, p->perc_identity, p->frag_len, p->reference_size);
+  BANI_CATCH
+}
+
+int bani_stat_min_hits_relaxed(int s, int k, float pid)
+{
+  BANI_TRY
+  if (s < 1 || k < 1) fail(BANI_ERR_ARG, "bad arguments");
+  return stat_min_hits_relaxed(s, k, pid);
+  BANI_CATCH
+}
+
+int bani_stat_identity(int shared, int s, int k, float *identity, float *upper)
+{
+  BANI_TRY
+  if (s < 1 || k < 1 || shared < 0 || shared > s || !identity || !upper) fail(BANI_ERR_ARG, "bad arguments");
+  stat_identity(shared, s, k, identity, upper);
+  return BANI_OK;
+  BANI_CATCH
+}
+
+int bani_ctx_create(int device, const bani_params *p, bani_ctx **out)
+{
+  BANI_TRY
+  if (!p || !out) fail(BANI_ERR_ARG, "null argument");
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { (void)cudaGetLastError(); fail(BANI_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)"); }
+  if (device < 0 || device >= n) fail(BANI_ERR_ARG, "device %d out of range (%d devices)", device, n);
+  BANI_CUDA(cudaSetDevice(device));
+  std::unique_ptr<bani_ctx> c(new bani_ctx());
+  c->c.device = device;
+  c->c.prm = *p;
+  if (c->c.prm.kmer_size < 1 || c->c.prm.kmer_size > 32) fail(BANI_ERR_LIMIT, "k-mer size %d outside [1, 32]", c->c.prm.kmer_size);
+  if (c->c.prm.frag_len < 1) fail(BANI_ERR_ARG, "fragment length must be positive");
+  if (c->c.prm.window_size <= 0)
+    c->c.prm.window_size = stat_recommended_window_size(p->p_value, p->kmer_size, p->perc_identity, p->frag_len, p->reference_size);
+  cudaDeviceProp prop;
+  BANI_CUDA(cudaGetDeviceProperties(&prop, device));
+  c->c.smCount = prop.multiProcessorCount;
+  BANI_CUDA(cudaStreamCreateWithFlags(&c->c.stream, cudaStreamNonBlocking));
+  cudaMemPool_t pool;
+  BANI_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+  uint64_t thr = UINT64_MAX;
+  BANI_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  *out = c.release();
+  return BANI_OK;
+  BANI_CATCH
+}
+
+void bani_ctx_destroy(bani_ctx *ctx)
+{
+  if (!ctx) return;
+  cudaSetDevice(ctx->c.device);
+  cudaStreamSynchronize(ctx->c.stream);
+  ctx->c.d_minHits.release(); ctx->c.d_rowOff.release(); ctx->c.d_ident.release(); ctx->c.d_upper.release();
+  cudaStreamSynchronize(ctx->c.stream);
+  cudaStreamDestroy(ctx->c.stream);
+  delete ctx;
+}
+
+int bani_ctx_params(const bani_ctx *ctx, bani_params *out)
+{
+  if (!ctx || !out) { set_last_error("null argument"); return BANI_ERR_ARG; }
+  *out = ctx->c.prm; return BANI_OK;
+}
+
+int bani_ctx_sync(bani_ctx *ctx)
+{
+  BANI_TRY
+  if (!ctx) fail(BANI_ERR_ARG, "null context");
+  BANI_CUDA(cudaSetDevice(ctx->c.device));
+  BANI_CUDA(cudaStreamSynchronize(ctx->c.stream));
+  return BANI_OK;
+  BANI_CATCH
+}
+
+void *bani_ctx_stream(bani_ctx *ctx) { return ctx ? (void *)ctx->c.stream : nullptr; }
+
+int bani_host_alloc(size_t bytes, void **out)
+{
+  BANI_TRY
+  if (!out) fail(BANI_ERR_ARG, "null argument");
+  BANI_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+  return BANI_OK;
+  BANI_CATCH
+}
+void bani_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+int bani_genome_create_batch(bani_ctx *ctx, int32_t n_genomes, const int32_t *gen_off, const int64_t *off,
+                             const uint8_t *seq, bani_genome **out)
+{
+  BANI_TRY
+  if (!ctx || !out || n_genomes < 0 || (n_genomes && (!gen_off || !off))) fail(BANI_ERR_ARG, "null argument");
+  BANI_CUDA(cudaSetDevice(ctx->c.device));
+  for (int g = 0; g < n_genomes; g++) {
+    if (gen_off[g + 1] < gen_off[g]) fail(BANI_ERR_ARG, "genome offsets must ascend");
+    for (int c = gen_off[g]; c < gen_off[g + 1]; c++) if (off[c + 1] < off[c]) fail(BANI_ERR_ARG, "contig offsets must ascend");
+  }
+  if (n_genomes && off[gen_off[n_genomes]] > off[gen_off[0]] && !seq) fail(BANI_ERR_ARG, "null sequence buffer");
+  std::vector<Genome *> gs(n_genomes, nullptr);
+  genome_create_batch(&ctx->c, n_genomes, gen_off, off, seq, gs.data());
+  for (int g = 0; g < n_genomes; g++) {
+    // bani_genome is a thin wrapper so that the handle type stays opaque in C
+    bani_genome *h = new bani_genome();
+    h->g = std::move(*gs[g]);
+    delete gs[g];
+    out[g] = h;
+  }
+  return BANI_OK;
+  BANI_CATCH
+}
+
+int bani_genome_create(bani_ctx *ctx, int32_t n_contigs, const int64_t *off, const uint8_t *seq, bani_genome **out)
+{
+  int32_t go[2] = {0, n_contigs};
+  if (n_contigs < 0) { set_last_error("negative contig count"); return BANI_ERR_ARG; }
+  int64_t zero[1] = {0};
+  return bani_genome_create_batch(ctx, 1, go, n_contigs ? off : zero, seq, out);
+}
+
+void bani_genome_destroy(bani_genome *g)
+{
+  if (!g) return;
+  cudaSetDevice(g->g.device);
+  delete g;
+}
+
+int bani_genome_info(const bani_genome *g, int32_t *n_contigs, uint64_t *total_len, uint64_t *n_exceptions, uint64_t *n_fragments)
+{
+  if (!g) { set_last_error("null genome"); return BANI_ERR_ARG; }
+  if (n_contigs) *n_contigs = g->g.nContigs;
+  if (total_len) *total_len = g->g.totalLen;
+  if (n_exceptions) *n_exceptions = g->g.nExc;
+  if (n_fragments) *n_fragments = 0;
+  return BANI_OK;
+}
+
+int bani_genome_decode(bani_ctx *ctx, const bani_genome *g, int32_t contig, uint8_t *out, int64_t cap)
+{
+  BANI_TRY
+  if (!ctx || !g || !out) fail(BANI_ERR_ARG, "null argument");
+  BANI_CUDA(cudaSetDevice(ctx->c.device));
+  genome_decode(&ctx->c, &g->g, contig, out, cap);
+  return BANI_OK;
+  BANI_CATCH
+}
+
+int bani_index_build(bani_ctx *ctx, bani_genome *const *refs, int32_t n_refs, bani_index **out)
+{
+  BANI_TRY
+  if (!ctx || !out || n_refs < 0 || (n_refs && !refs)) fail(BANI_ERR_ARG, "null argument");
+  BANI_CUDA(cudaSetDevice(ctx->c.device));
+  std::vector<Genome *> gs(n_refs);
+  for (int i = 0; i < n_refs; i++) { if (!refs[i]) fail(BANI_ERR_ARG, "null genome handle"); gs[i] = &refs[i]->g; }
+  Index *ix = index_build(&ctx->c, gs.data(), n_refs);
+  bani_index *h = new bani_index(); h->ix = ix; *out = h;
+  return BANI_OK;
+  BANI_CATCH
+}
+
+void bani_index_destroy(bani_index *ix)
+{
+  if (!ix) return;
+  if (ix->ix) { cudaSetDevice(ix->ix->device); delete ix->ix; }
+  delete ix;
+}
+
+int bani_index_stats(const bani_index *ix, uint64_t *n_minimizers, uint64_t *n_unique, uint64_t *total_len,
+                     uint64_t *n_contigs, uint64_t *n_genomes)
+{
+  if (!ix || !ix->ix) { set_last_error("null index"); return BANI_ERR_ARG; }
+  if (n_minimizers) *n_minimizers = ix->ix->M;
+  if (n_unique) *n_unique = ix->ix->U;
+  if (total_len) *total_len = ix->ix->totalLen;
+  if (n_contigs) *n_contigs = (uint64_t)ix->ix->nContigs;
+  if (n_genomes) *n_genomes = (uint64_t)ix->ix->nGenomes;
+  return BANI_OK;
+}
+
+int bani_index_minimizers(bani_ctx *ctx, const bani_index *ixh, bani_minimizer *out, uint64_t cap)
+{
+  BANI_TRY
+  if (!ctx || !ixh || !ixh->ix || (!out && cap)) fail(BANI_ERR_ARG, "null argument");
+  const Index *ix = ixh->ix;
+  if (cap < ix->M) fail(BANI_ERR_ARG, "output buffer too small (%llu < %llu)", (unsigned long long)cap, (unsigned long long)ix->M);
+  BANI_CUDA(cudaSetDevice(ctx->c.device));
+  const size_t M = ix->M;
+  if (!M) return BANI_OK;
+  std::vector<uint32_t> h(M); std::vector<int32_t> s(M), w(M);
+  BANI_CUDA(cudaStreamSynchronize(ctx->c.stream));
+  BANI_CUDA(cudaMemcpy(h.data(), ix->hash.p, 4 * M, cudaMemcpyDeviceToHost));
+  BANI_CUDA(cudaMemcpy(s.data(), ix->seqId.p, 4 * M, cudaMemcpyDeviceToHost));
+  BANI_CUDA(cudaMemcpy(w.data(), ix->wpos.p, 4 * M, cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < M; i++) { out[i].hash = h[i]; out[i].seqId = s[i]; out[i].wpos = w[i]; }
+  return BANI_OK;
+  BANI_CATCH
+}
+
+int bani_index_lookup(bani_ctx *ctx, const bani_index *ixh, uint32_t hash, int32_t *seqId, int32_t *wpos, uint64_t cap, uint64_t *n)
+{
+  BANI_TRY
+  if (!ctx || !ixh || !ixh->ix || !n) fail(BANI_ERR_ARG, "null argument");
+  const Index *ix = ixh->ix;
+  BANI_CUDA(cudaSetDevice(ctx->c.device));
+  BANI_CUDA(cudaStreamSynchronize(ctx->c.stream));
+  *n = 0;
+  if (!ix->U) return BANI_OK;
+  // host-driven probe of the device structures (test hook; the mapping kernels do this on the device)
+  const uint32_t b = hash >> (32 - ix->dirBits);
+  uint32_t d[2];
+  BANI_CUDA(cudaMemcpy(d, ix->dir.p + b, 8, cudaMemcpyDeviceToHost));
+  if (d[1] <= d[0]) return BANI_OK;
+  std::vector<uint32_t> keys(d[1] - d[0]);
+  BANI_CUDA(cudaMemcpy(keys.data(), ix->ukeys.p + d[0], 4 * keys.size(), cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < keys.size(); i++) if (keys[i] == hash) {
+    uint32_t o[2];
+    BANI_CUDA(cudaMemcpy(o, ix->uoff.p + d[0] + i, 8, cudaMemcpyDeviceToHost));
+    const uint64_t cnt = o[1] - o[0];
+    *n = cnt;
+    const uint64_t m = cnt < cap ? cnt : cap;
+    std::vector<uint32_t> pi(m);
+    if (m) BANI_CUDA(cudaMemcpy(pi.data(), ix->posIdx.p + o[0], 4 * m, cudaMemcpyDeviceToHost));
+    for (uint64_t j = 0; j < m; j++) {
+      BANI_CUDA(cudaMemcpy(&seqId[j], ix->seqId.p + pi[j], 4, cudaMemcpyDeviceToHost));
+      BANI_CUDA(cudaMemcpy(&wpos[j], ix->wpos.p + pi[j], 4, cudaMemcpyDeviceToHost));
+    }
+    break;
+  }
+  return BANI_OK;
+  BANI_CATCH
+}
+
+int bani_map_genome(bani_ctx *ctx, const bani_index *ix, const bani_genome *query, bani_mapping **rows, uint64_t *n_rows,
+                    uint64_t *total_query_fragments, bani_map_counters *counters)
+{
+  BANI_TRY
+  if (!ctx || !ix || !ix->ix || !query || !rows || !n_rows) fail(BANI_ERR_ARG, "null argument");
+  BANI_CUDA(cudaSetDevice(ctx->c.device));
+  MapOutput mo;
+  const Genome *q = &query->g;
+  map_queries(&ctx->c, ix->ix, &q, 1, true, false, mo);
+  *n_rows = mo.rows.size();
+  *rows = nullptr;
+  if (!mo.rows.empty()) {
+    *rows = (bani_mapping *)malloc(sizeof(bani_mapping) * mo.rows.size());
+    if (!*rows) fail(BANI_ERR_NOMEM, "host allocation failed");
+    memcpy(*rows, mo.rows.data(), sizeof(bani_mapping) * mo.rows.size());
+  }
+  if (total_query_fragments) *total_query_fragments = mo.totalQueryFragments[0];
+  if (counters) *counters = mo.ctr;
+  return BANI_OK;
+  BANI_CATCH
+}
+
+int bani_map_cgi(bani_ctx *ctx, const bani_index *ix, bani_genome *const *queries, int32_t n_queries,
+                 bani_cgi_result **results, uint64_t *n_results, uint64_t *total_query_fragments, bani_map_counters *counters)
+{
+  BANI_TRY
+  if (!ctx || !ix || !ix->ix || n_queries < 0 || (n_queries && !queries) || !results || !n_results) fail(BANI_ERR_ARG, "null argument");
+  BANI_CUDA(cudaSetDevice(ctx->c.device));
+  std::vector<const Genome *> qs(n_queries);
+  for (int i = 0; i < n_queries; i++) { if (!queries[i]) fail(BANI_ERR_ARG, "null genome handle"); qs[i] = &queries[i]->g; }
+  MapOutput mo;
+  map_queries(&ctx->c, ix->ix, qs.data(), n_queries, false, true, mo);
+  *n_results = mo.cgi.size();
+  *results = nullptr;
+  if (!mo.cgi.empty()) {
+    *results = (bani_cgi_result *)malloc(sizeof(bani_cgi_result) * mo.cgi.size());
+    if (!*results) fail(BANI_ERR_NOMEM, "host allocation failed");
+    memcpy(*results, mo.cgi.data(), sizeof(bani_cgi_result) * mo.cgi.size());
+  }
+  if (total_query_fragments) for (int i = 0; i < n_queries; i++) total_query_fragments[i] = mo.totalQueryFragments[i];
+  if (counters) *counters = mo.ctr;
+  return BANI_OK;
+  BANI_CATCH
+}
+
+void bani_free(void *p) { free(p); }
+
+int bani_synth_genome(bani_ctx *ctx, uint64_t seed, uint32_t ancestor_id, uint32_t strain_id, uint32_t sub_rate_ppm,
+                      int64_t len, uint8_t *host_out)
+{
+  BANI_TRY
+  if (!ctx || (len > 0 && !host_out) || len < 0) fail(BANI_ERR_ARG, "bad argument");
+  BANI_CUDA(cudaSetDevice(ctx->c.device));
+  synth_genome(&ctx->c, seed, ancestor_id, strain_id, sub_rate_ppm, len, host_out);
+  return BANI_OK;
+  BANI_CATCH
+}
+
+} // extern "C"

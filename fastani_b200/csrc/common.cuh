@@ -1,0 +1,175 @@
+// common.cuh -- internal types shared by the translation units of libfastani_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include <memory>
+#include <stdexcept>
+#include <cstdio>
+#include <cstdarg>
+#include "../../include/fastani_b200.h"
+
+namespace bani {
+
+// ---------------------------------------------------------------- errors
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+
+void set_last_error(const std::string &m);
+
+[[noreturn]] inline void fail(int code, const char *fmt, ...)
+{
+  char buf[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  throw Error(code, buf);
+}
+
+#define BANI_CUDA(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) \
+  ::bani::fail(BANI_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+// ---------------------------------------------------------------- device memory
+// Stream-ordered allocation from the device's default memory pool (release
+// threshold raised in Ctx so freed blocks are recycled, not returned to the OS).
+template <typename T>
+struct DevBuf {
+  T *p = nullptr; size_t n = 0; cudaStream_t st = nullptr;
+  DevBuf() {}
+  DevBuf(size_t n_, cudaStream_t s) { alloc(n_, s); }
+  DevBuf(const DevBuf &) = delete; DevBuf &operator=(const DevBuf &) = delete;
+  DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), st(o.st) { o.p = nullptr; o.n = 0; }
+  DevBuf &operator=(DevBuf &&o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; st = o.st; o.p = nullptr; o.n = 0; } return *this; }
+  ~DevBuf() { release(); }
+  void alloc(size_t n_, cudaStream_t s)
+  {
+    release(); n = n_; st = s;
+    if (n == 0) return;
+    cudaError_t e = cudaMallocAsync((void **)&p, n * sizeof(T), s);
+    if (e != cudaSuccess) { p = nullptr; size_t want = n * sizeof(T); n = 0; (void)cudaGetLastError();
+      fail(BANI_ERR_NOMEM, "device allocation of %zu bytes failed: %s", want, cudaGetErrorString(e)); }
+  }
+  void release() { if (p) { cudaFreeAsync(p, st); p = nullptr; } n = 0; }
+  size_t bytes() const { return n * sizeof(T); }
+};
+
+// ---------------------------------------------------------------- statistics (host)
+int   stat_recommended_window_size(double p_value, int k, float identity, int fragLen, uint64_t refSize);
+int   stat_min_hits_relaxed(int s, int k, float identity);
+void  stat_identity(int shared, int s, int k, float *id, float *ub);
+
+// LUT rows consumed by the mapping kernels: for sketch size s,
+//   minHits[s]            = max(1, estimateMinimumHitsRelaxed(s, k, pid))
+//   rowOff[s] .. +s+1     : identity[x], upper[x] for x = 0..s
+struct StatLut {
+  int k = 0; float pid = 0;
+  std::vector<int32_t> minHits;     // index s (0 unused)
+  std::vector<uint32_t> rowOff;     // index s -> offset into ident/upper
+  std::vector<float> ident, upper;
+  int smax = 0;
+  void ensure(int s_needed);        // extends rows up to s_needed (host)
+};
+
+// ---------------------------------------------------------------- genomes
+// Per-contig descriptor consumed by the sketch kernel.  A query fragment is the
+// same thing with a non-zero startBase and len = fragLen.
+struct SeqDesc {
+  const uint32_t *packed;   // first 2-bit word of the parent contig (16 bases / word)
+  const uint32_t *excPos;   // sorted contig-relative positions of non-ACGT bytes (parent contig)
+  const uint8_t  *excByte;  // their (upper-cased) bytes
+  int32_t nExc;
+  int32_t startBase;        // offset of this sequence inside the parent contig
+  int32_t len;              // bases
+  int32_t seqId;            // ordinal written to the records
+};
+
+struct Genome {
+  int device = 0;
+  int32_t nContigs = 0;
+  std::vector<int32_t> len;          // per contig
+  std::vector<int64_t> wordOff;      // per contig, into packed (multiple of 4 words)
+  std::vector<int64_t> excOff;       // per contig +1, into exc arrays
+  uint64_t totalLen = 0, nExc = 0;
+  DevBuf<uint32_t> packed;
+  DevBuf<uint32_t> excPos;
+  DevBuf<uint8_t>  excByte;
+};
+
+struct Ctx;
+
+// ---------------------------------------------------------------- index (HP1 output)
+struct Index {
+  int device = 0;
+  uint64_t M = 0, U = 0, totalLen = 0;
+  int32_t nContigs = 0, nGenomes = 0;
+  int dirBits = 0;
+  // position-ordered records (== Sketch::minimizerIndex as SoA) + same-hash links
+  DevBuf<uint32_t> hash; DevBuf<int32_t> wpos; DevBuf<int32_t> seqId; DevBuf<uint32_t> link;
+  DevBuf<uint32_t> contigRecOff;     // nContigs+1: first record of each contig
+  DevBuf<int32_t>  contigGenome;     // nContigs: genome ordinal of a contig (reviseRefIdToGenomeId)
+  DevBuf<uint32_t> contigBinOff;     // nContigs+1: prefix of #position-bins per contig (CGI)
+  // hash-ordered lookup side (== Sketch::minimizerPosLookupIndex)
+  DevBuf<uint32_t> ukeys;            // U unique hashes ascending
+  DevBuf<uint32_t> uoff;             // U+1 offsets into posIdx
+  DevBuf<uint32_t> posIdx;           // M record indices, sorted by (hash, record index)
+  DevBuf<uint32_t> dir;              // (1<<dirBits)+1 bucket directory over the top bits of the hash
+  std::vector<int32_t> contigLen;    // host copies
+  std::vector<int32_t> seqsByFile;   // cumulative contig count per genome (sequencesByFileInfo)
+  uint64_t totalBins = 0;
+};
+
+struct Ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bani_params prm{};
+  int smCount = 0;
+  StatLut lut;
+  DevBuf<int32_t> d_minHits; DevBuf<uint32_t> d_rowOff; DevBuf<float> d_ident, d_upper;
+  int lutUploaded = 0;
+  void upload_lut(int smax);
+};
+
+// ---------------------------------------------------------------- kernels' host entry points
+// pack.cu
+void genome_create_batch(Ctx *ctx, int32_t nGenomes, const int32_t *genOff, const int64_t *off,
+                         const uint8_t *seq, Genome **out);
+void genome_decode(Ctx *ctx, const Genome *g, int32_t contig, uint8_t *out, int64_t cap);
+
+// sketch.cu : windowed minimizers of a list of sequences, records compacted in
+// (sequence, wpos) order.  Outputs may be null (skipped).  Returns total records
+// (which may exceed `cap`; only the first cap are stored).
+uint64_t sketch_sequences(Ctx *ctx, const SeqDesc *d_desc, int32_t nSeq, const int32_t *h_len,
+                          uint32_t *o_hash, int32_t *o_wpos, int32_t *o_seqId, uint64_t cap,
+                          uint32_t *o_segStart /* nSeq+1 */);
+
+// index.cu
+Index *index_build(Ctx *ctx, Genome *const *refs, int32_t nRefs);
+
+// map.cu
+struct MapOutput {
+  std::vector<bani_mapping> rows;               // when wantRows
+  std::vector<bani_cgi_result> cgi;             // when wantCgi
+  std::vector<uint64_t> totalQueryFragments;    // per query
+  bani_map_counters ctr{};
+};
+void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_t nq,
+                 bool wantRows, bool wantCgi, MapOutput &out);
+
+// synth.cu
+void synth_genome(Ctx *ctx, uint64_t seed, uint32_t ancestor, uint32_t strain, uint32_t ppm,
+                  int64_t len, uint8_t *hostOut);
+
+// CUB-backed primitives (cubops.cu; kept in one TU because CUB compiles slowly)
+size_t cub_sort_pairs_u32_temp(size_t n);
+void   cub_sort_pairs_u32(void *temp, size_t tempBytes, const uint32_t *kin, uint32_t *kout,
+                          const uint32_t *vin, uint32_t *vout, size_t n, int endBit, cudaStream_t s);
+size_t cub_sort_keys_u64_temp(size_t n);
+void   cub_sort_keys_u64(void *temp, size_t tempBytes, const uint64_t *kin, uint64_t *kout, size_t n,
+                         int beginBit, int endBit, cudaStream_t s);
+size_t cub_scan_u32_temp(size_t n);
+void   cub_exclusive_sum_u32(void *temp, size_t tempBytes, const uint32_t *in, uint32_t *out, size_t n, cudaStream_t s);
+size_t cub_scan_u64_temp(size_t n);
+void   cub_exclusive_sum_u32_to_u64(void *temp, size_t tempBytes, const uint32_t *in, uint64_t *out, size_t n, cudaStream_t s);
+
+} // namespace bani

@@ -1,0 +1,182 @@
+/* fastani_b200.h -- C ABI of the B200-native ANI hot path.
+ *
+ * This is the drop-in boundary for the two data-parallel hot paths of FastANI
+ * (reference citations are relative to the upstream tree, ParBLiSS/FastANI):
+ *
+ *   HP1  reference index build   skch::Sketch::Sketch(const Parameters&)
+ *                                 src/map/include/winSketch.hpp:109-115
+ *   HP2  query mapping           skch::Map::Map(const Parameters&, const Sketch&,
+ *                                 uint64_t& totalQueryFragments, int queryno, callback)
+ *                                 src/map/include/computeMap.hpp:93-102
+ *   (+)  per-pair reduction      cgi::computeCGI
+ *                                 src/cgi/include/computeCoreIdentity.hpp:166-298
+ *
+ * The reference has no FFI layer; its seam is those two constructors and one
+ * callback.  The entry points below are what a binding for that seam needs:
+ * plain pointers and sizes, no C++ or torch types.  All device work runs on the
+ * CUDA device the context was created on (sm_100a kernels); there is NO CPU
+ * fallback -- every call fails with BANI_ERR_CUDA if no device is usable.
+ *
+ * Conventions: every function returns 0 (BANI_OK) or a negative bani_status;
+ * bani_last_error() gives a thread-local message for the last failure.  The
+ * library allocates outputs; the caller frees them through the library.
+ * Handles are not thread-safe individually; distinct contexts may be used from
+ * distinct threads concurrently.
+ */
+#ifndef FASTANI_B200_H
+#define FASTANI_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BANI_API __attribute__((visibility("default")))
+
+typedef enum {
+  BANI_OK = 0,
+  BANI_ERR_ARG = -1,       /* invalid argument */
+  BANI_ERR_CUDA = -2,      /* CUDA runtime failure / no usable device */
+  BANI_ERR_NOMEM = -3,     /* host or device allocation failed */
+  BANI_ERR_LIMIT = -4,     /* an implementation limit was exceeded (message says which) */
+  BANI_ERR_INTERNAL = -5
+} bani_status;
+
+/* skch::Parameters, src/map/include/map_parameters.hpp:22-41 -- the fields the
+ * hot path reads.  Zero-initialise, then call bani_params_default(). */
+typedef struct {
+  int32_t  kmer_size;          /* kmerSize            (default 16) */
+  int32_t  window_size;        /* windowSize; <=0 => Stat::recommendedWindowSize */
+  int32_t  frag_len;           /* minReadLength       (default 3000) */
+  float    perc_identity;      /* percentageIdentity  (default 80) */
+  double   p_value;            /* p_value             (default 1e-3) */
+  uint64_t reference_size;     /* referenceSize       (default 5000000) */
+  int32_t  reserved[8];
+} bani_params;
+
+/* skch::MappingResult, src/map/include/base_types.hpp:89-102 (44 bytes, same field order) */
+typedef struct {
+  int32_t queryLen, refStartPos, refEndPos, queryStartPos, queryEndPos;
+  int32_t refSeqId, querySeqId;
+  float   nucIdentity, nucIdentityUpperBound;
+  int32_t sketchSize, conservedSketches;
+} bani_mapping;
+
+/* skch::MinimizerInfo, src/map/include/base_types.hpp:21-53 (12 bytes) */
+typedef struct { uint32_t hash; int32_t seqId; int32_t wpos; } bani_minimizer;
+
+/* cgi::CGI_Results, src/cgi/include/cgid_types.hpp:68-80.  refGenomeId is the
+ * ordinal of the genome inside the index it was mapped against. */
+typedef struct {
+  int32_t refGenomeId, qryGenomeId, countSeq, totalQueryFragments;
+  float   identity;
+} bani_cgi_result;
+
+/* Integer work counters of one mapping call; SURVEY.md section 8(d) defines the
+ * algorithmic bytes of HP2 from these (same meaning as the oracle's counters). */
+typedef struct {
+  uint64_t fragments;     /* F   query fragments considered                      */
+  uint64_t sum_s;         /* sum of unique query minimizers probed               */
+  uint64_t hits;          /* H   index positions gathered                        */
+  uint64_t candidates;    /* L1 candidate regions                                */
+  uint64_t n2;            /* position-ordered records scanned over all candidates*/
+  uint64_t mappings;      /* P   mapping records kept                            */
+  uint64_t reserved[4];
+} bani_map_counters;
+
+typedef struct bani_ctx    bani_ctx;      /* one per CUDA device: stream, scratch, statistic LUTs */
+typedef struct bani_genome bani_genome;   /* a genome resident in HBM: 2-bit packed contigs + exceptions */
+typedef struct bani_index  bani_index;    /* a reference index resident in HBM (HP1 output)             */
+
+BANI_API const char *bani_last_error(void);
+BANI_API const char *bani_version(void);
+BANI_API void bani_params_default(bani_params *p);
+
+/* Stat::recommendedWindowSize, src/map/include/map_stats.hpp:226-256 (host, double math). */
+BANI_API int bani_recommended_window_size(const bani_params *p);
+/* Stat::estimateMinimumHitsRelaxed (map_stats.hpp:142-167) and the identity /
+ * upper-bound expressions of Map::doL2Mapping (computeMap.hpp:375-381): exposed
+ * so the statistic LUT the kernels consume can be checked on its own. */
+BANI_API int bani_stat_min_hits_relaxed(int s, int k, float perc_identity);
+BANI_API int bani_stat_identity(int shared, int s, int k, float *identity, float *upper_bound);
+
+/* ---- context -------------------------------------------------------------- */
+BANI_API int  bani_ctx_create(int device, const bani_params *p, bani_ctx **out);
+BANI_API void bani_ctx_destroy(bani_ctx *ctx);
+BANI_API int  bani_ctx_params(const bani_ctx *ctx, bani_params *out);   /* window_size resolved */
+BANI_API int  bani_ctx_sync(bani_ctx *ctx);
+/* Raw CUDA stream (cudaStream_t) every launch of this context goes to; for event timing. */
+BANI_API void *bani_ctx_stream(bani_ctx *ctx);
+
+/* Pinned host memory for staging genomes (optional; pageable buffers also work). */
+BANI_API int  bani_host_alloc(size_t bytes, void **out);
+BANI_API void bani_host_free(void *p);
+
+/* ---- genome ingest --------------------------------------------------------
+ * A genome is what one FASTA file holds: n_contigs sequences given as the raw
+ * bytes kseq_read() yields (seq->seq.s / seq->seq.l, winSketch.hpp:147-150):
+ * any case, any IUPAC or other byte.  Bytes are upper-cased (a-z only,
+ * commonFunc.hpp:57-66) and packed on the GPU to 2 bits/base; every non-ACGT
+ * byte is carried out of band so hashing sees exactly the reference's bytes.
+ * `seq` is one host buffer; contig c occupies [off[c], off[c+1]).
+ * Contigs keep their ordinal even when shorter than k or w (winSketch.hpp:150-164). */
+BANI_API int  bani_genome_create(bani_ctx *ctx, int32_t n_contigs, const int64_t *off,
+                                 const uint8_t *seq, bani_genome **out);
+/* Several genomes in one call (one device synchronisation for the whole batch).
+ * genome g owns contigs [gen_off[g], gen_off[g+1]) of the off[] table. */
+BANI_API int  bani_genome_create_batch(bani_ctx *ctx, int32_t n_genomes, const int32_t *gen_off,
+                                       const int64_t *off, const uint8_t *seq, bani_genome **out);
+BANI_API void bani_genome_destroy(bani_genome *g);
+BANI_API int  bani_genome_info(const bani_genome *g, int32_t *n_contigs, uint64_t *total_len,
+                               uint64_t *n_exceptions, uint64_t *n_fragments);
+/* Device -> host decode of one contig back to (upper-cased) ASCII; test hook for the packer. */
+BANI_API int  bani_genome_decode(bani_ctx *ctx, const bani_genome *g, int32_t contig, uint8_t *out, int64_t cap);
+
+/* ---- HP1: reference index build -------------------------------------------
+ * Sketch::build + Sketch::index (winSketch.hpp:124-193) over the given genomes
+ * in order; seqId runs over all contigs of all genomes (sequencesByFileInfo,
+ * winSketch.hpp:75,167).  An empty list builds an empty index. */
+BANI_API int  bani_index_build(bani_ctx *ctx, bani_genome *const *refs, int32_t n_refs, bani_index **out);
+BANI_API void bani_index_destroy(bani_index *ix);
+/* Totals needed by Sketch::sanityCheck (winSketch.hpp:298-318) and the log lines. */
+BANI_API int  bani_index_stats(const bani_index *ix, uint64_t *n_minimizers, uint64_t *n_unique,
+                               uint64_t *total_len, uint64_t *n_contigs, uint64_t *n_genomes);
+/* The position-ordered minimizer table (== Sketch::minimizerIndex, winSketch.hpp:94), copied to host. */
+BANI_API int  bani_index_minimizers(bani_ctx *ctx, const bani_index *ix, bani_minimizer *out, uint64_t cap);
+/* The lookup side (== Sketch::minimizerPosLookupIndex, winSketch.hpp:84): all positions of one hash.
+ * Returns the count through *n; writes at most cap (seqId, wpos) pairs. */
+BANI_API int  bani_index_lookup(bani_ctx *ctx, const bani_index *ix, uint32_t hash,
+                                int32_t *seqId, int32_t *wpos, uint64_t cap, uint64_t *n);
+
+/* ---- HP2: query mapping ---------------------------------------------------
+ * Map::mapQuery (computeMap.hpp:112-196) for one query genome: every mapping the
+ * reference would pass to its callback, in the same (fragment, candidate) order.
+ * *rows is allocated by the library (free with bani_free). */
+BANI_API int  bani_map_genome(bani_ctx *ctx, const bani_index *ix, const bani_genome *query,
+                              bani_mapping **rows, uint64_t *n_rows,
+                              uint64_t *total_query_fragments, bani_map_counters *counters);
+
+/* Map + cgi::computeCGI fused on the device for a batch of query genomes: one
+ * bani_cgi_result per (query, reference genome) pair with at least one 2-way
+ * mapping, ordered by (query, refGenomeId); qryGenomeId = position in `queries`.
+ * total_query_fragments (optional, n_queries entries) is filled per query. */
+BANI_API int  bani_map_cgi(bani_ctx *ctx, const bani_index *ix, bani_genome *const *queries, int32_t n_queries,
+                           bani_cgi_result **results, uint64_t *n_results,
+                           uint64_t *total_query_fragments, bani_map_counters *counters);
+
+BANI_API void bani_free(void *p);
+
+/* ---- bench utilities -------------------------------------------------------
+ * Deterministic synthetic genome, generated on the device and written to a host
+ * buffer as upper-case ACGT ASCII (counter-based generator; fastani_b200/synth.py
+ * is the same function in numpy).  ancestor_id picks the ancestor sequence,
+ * strain_id the substitution stream, sub_rate_ppm the per-base substitution rate. */
+BANI_API int  bani_synth_genome(bani_ctx *ctx, uint64_t seed, uint32_t ancestor_id, uint32_t strain_id,
+                                uint32_t sub_rate_ppm, int64_t len, uint8_t *host_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FASTANI_B200_H */
