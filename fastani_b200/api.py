@@ -73,6 +73,9 @@ def load_library():
         "bani_ctx_params": (C.c_int, [vp, P(_Params)]),
         "bani_ctx_sync": (C.c_int, [vp]),
         "bani_ctx_stream": (vp, [vp]),
+        "bani_ctx_launch_count": (u64, [vp]),
+        "bani_ctx_profile_enable": (C.c_int, [vp, C.c_int]),
+        "bani_ctx_profile_read": (C.c_int, [vp, vp, vp, vp, vp, i32, P(i32)]),
         "bani_host_alloc": (C.c_int, [C.c_size_t, P(vp)]),
         "bani_host_free": (None, [vp]),
         "bani_genome_create": (C.c_int, [vp, i32, vp, vp, P(vp)]),
@@ -101,7 +104,7 @@ def load_library():
 EXPORTED_SYMBOLS = [
     "bani_last_error", "bani_version", "bani_params_default", "bani_recommended_window_size",
     "bani_stat_min_hits_relaxed", "bani_stat_identity", "bani_ctx_create", "bani_ctx_destroy", "bani_ctx_params",
-    "bani_ctx_sync", "bani_ctx_stream", "bani_host_alloc", "bani_host_free", "bani_genome_create",
+    "bani_ctx_sync", "bani_ctx_stream", "bani_ctx_launch_count", "bani_ctx_profile_enable", "bani_ctx_profile_read", "bani_host_alloc", "bani_host_free", "bani_genome_create",
     "bani_genome_create_batch", "bani_genome_destroy", "bani_genome_info", "bani_genome_decode", "bani_index_build",
     "bani_index_destroy", "bani_index_stats", "bani_index_minimizers", "bani_index_lookup", "bani_map_genome",
     "bani_map_cgi", "bani_free", "bani_synth_genome"]
@@ -166,6 +169,20 @@ class Context:
     @property
     def stream(self):
         return self.lib.bani_ctx_stream(self.h)
+
+    def launch_count(self):
+        return int(self.lib.bani_ctx_launch_count(self.h))
+
+    def profile(self, on=True):
+        _check(self.lib.bani_ctx_profile_enable(self.h, 1 if on else 0))
+
+    def profile_read(self):
+        """{stage: (ms, algorithmic_bytes, launches)} accumulated since the last read."""
+        nmax = 64
+        names = (C.c_char * 32 * nmax)()
+        ms = (C.c_double * nmax)(); by = (C.c_double * nmax)(); la = (C.c_int32 * nmax)(); n = C.c_int32()
+        _check(self.lib.bani_ctx_profile_read(self.h, names, ms, by, la, nmax, C.byref(n)))
+        return {names[i].value.decode(): (ms[i], by[i], la[i]) for i in range(n.value)}
 
     def close(self):
         if getattr(self, "h", None):

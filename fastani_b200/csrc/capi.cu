@@ -112,6 +112,40 @@ int bani_ctx_sync(bani_ctx *ctx)
   BANI_CATCH
 }
 
+int bani_ctx_profile_enable(bani_ctx *ctx, int on)
+{
+  if (!ctx) { set_last_error("null context"); return BANI_ERR_ARG; }
+  ctx->c.profiling = on != 0;
+  return BANI_OK;
+}
+
+int bani_ctx_profile_read(bani_ctx *ctx, char (*names)[32], double *ms, double *algo_bytes, int32_t *launches,
+                          int32_t n_max, int32_t *n)
+{
+  BANI_TRY
+  if (!ctx || !n) fail(BANI_ERR_ARG, "null argument");
+  BANI_CUDA(cudaSetDevice(ctx->c.device));
+  BANI_CUDA(cudaStreamSynchronize(ctx->c.stream));
+  int cnt = 0;
+  for (auto &e : ctx->c.profEvents) {
+    float t = 0; cudaEventElapsedTime(&t, e.a, e.b);
+    cudaEventDestroy(e.a); cudaEventDestroy(e.b);
+    int j = 0;
+    for (; j < cnt; j++) if (strncmp(names[j], e.name, 31) == 0) break;
+    if (j == cnt) {
+      if (cnt >= n_max) continue;
+      strncpy(names[j], e.name, 31); names[j][31] = 0; ms[j] = 0; algo_bytes[j] = 0; launches[j] = 0; cnt++;
+    }
+    ms[j] += t; algo_bytes[j] += e.bytes; launches[j] += 1;
+  }
+  ctx->c.profEvents.clear();
+  *n = cnt;
+  return BANI_OK;
+  BANI_CATCH
+}
+
+uint64_t bani_ctx_launch_count(const bani_ctx *ctx) { return ctx ? ctx->c.launches : 0; }
+
 void *bani_ctx_stream(bani_ctx *ctx) { return ctx ? (void *)ctx->c.stream : nullptr; }
 
 int bani_host_alloc(size_t bytes, void **out)

@@ -128,6 +128,27 @@ struct Ctx {
   DevBuf<int32_t> d_minHits; DevBuf<uint32_t> d_rowOff; DevBuf<float> d_ident, d_upper;
   int lutUploaded = 0;
   void upload_lut(int smax);
+  // optional per-stage device timing (CUDA events on `stream`), see bani_ctx_profile_*
+  uint64_t launches = 0;             // kernels of this library launched so far (CUB's not counted)
+  bool profiling = false;
+  struct ProfEv { const char *name; cudaEvent_t a, b; double bytes; };
+  std::vector<ProfEv> profEvents;
+};
+
+// RAII stage timer: records an event pair around a stage when profiling is on.
+struct Stage {
+  Ctx *c; size_t idx = (size_t)-1;
+  Stage(Ctx *ctx, const char *name, double algoBytes = 0) : c(ctx)
+  {
+    if (!c->profiling) return;
+    Ctx::ProfEv e; e.name = name; e.bytes = algoBytes;
+    cudaEventCreate(&e.a); cudaEventCreate(&e.b);
+    cudaEventRecord(e.a, c->stream);
+    idx = c->profEvents.size(); c->profEvents.push_back(e);
+  }
+  void bytes(double b) { if (idx != (size_t)-1) c->profEvents[idx].bytes = b; }
+  void stop() { if (idx != (size_t)-1) { cudaEventRecord(c->profEvents[idx].b, c->stream); idx = (size_t)-1; } }
+  ~Stage() { stop(); }
 };
 
 // ---------------------------------------------------------------- kernels' host entry points

@@ -118,6 +118,7 @@ Index *index_build(Ctx *ctx, Genome *const *refs, int32_t nRefs)
   if (nC == 0 || totalPos == 0) {
     // empty index: every lookup misses (a shard with no references, computeCoreIdentity.hpp:468-471)
     fill_u32<<<nblk(nC + 1), 256, 0, st>>>(ix->contigRecOff.p, 0, (uint64_t)nC + 1);
+    ctx->launches++;
     ix->dirBits = 8;
     ix->dir.alloc((1u << ix->dirBits) + 1, st);
     BANI_CUDA(cudaMemsetAsync(ix->dir.p, 0, 4 * ((1u << ix->dirBits) + 1), st));
@@ -140,6 +141,7 @@ Index *index_build(Ctx *ctx, Genome *const *refs, int32_t nRefs)
     for (int attempt = 0; attempt < 2; attempt++) {
       if (cap > 0xfffffff0ull) fail(BANI_ERR_LIMIT, "more than 2^32 minimizers in one index shard");
       th.alloc(cap, st); tw.alloc(cap, st); ts.alloc(cap, st);
+      Stage sg(ctx, "ref_sketch", (double)ix->totalLen / 4.0);
       M = sketch_sequences(ctx, d_desc.p, nC, ix->contigLen.data(), th.p, tw.p, ts.p, cap, ix->contigRecOff.p);
       if (M <= cap) break;
       cap = M;
@@ -168,13 +170,17 @@ Index *index_build(Ctx *ctx, Genome *const *refs, int32_t nRefs)
   }
   DevBuf<uint32_t> sortedHash(M, st), iota(M, st), head(M, st), scan(M, st);
   DevBuf<unsigned long long> d_U(1, st);
-  iota_kernel<<<nblk(M), 256, 0, st>>>(iota.p, M);
   {
+    Stage sg(ctx, "index_sort", 24.0 * M);
+    iota_kernel<<<nblk(M), 256, 0, st>>>(iota.p, M);
+    ctx->launches++;
     size_t tb = cub_sort_pairs_u32_temp(M);
     DevBuf<uint8_t> tmp(tb, st);
     cub_sort_pairs_u32(tmp.p, tb, ix->hash.p, sortedHash.p, iota.p, ix->posIdx.p, M, 32, st);
   }
+  Stage sgc(ctx, "index_compact", 16.0 * M);
   head_flags_kernel<<<nblk(M), 256, 0, st>>>(sortedHash.p, M, head.p);
+  ctx->launches++;
   {
     size_t tb = cub_scan_u32_temp(M);
     DevBuf<uint8_t> tmp(tb, st);
@@ -189,12 +195,16 @@ Index *index_build(Ctx *ctx, Genome *const *refs, int32_t nRefs)
   ix->U = U;
   ix->ukeys.alloc(U, st); ix->uoff.alloc(U + 1, st);
   unique_scatter_kernel<<<nblk(M), 256, 0, st>>>(sortedHash.p, head.p, scan.p, M, ix->ukeys.p, ix->uoff.p, d_U.p);
+  ctx->launches++;
   { uint32_t Mu = (uint32_t)M; BANI_CUDA(cudaMemcpyAsync(ix->uoff.p + U, &Mu, 4, cudaMemcpyHostToDevice, st)); }
   links_kernel<<<nblk(M), 256, 0, st>>>(sortedHash.p, ix->posIdx.p, M, ix->link.p);
+  ctx->launches++;
   int bits = 8; while (bits < 24 && (1ull << bits) < U) bits++;
   ix->dirBits = bits;
   ix->dir.alloc((1u << bits) + 1, st);
   dir_kernel<<<nblk(U), 256, 0, st>>>(ix->ukeys.p, (uint32_t)U, bits, ix->dir.p);
+  ctx->launches++;
+  sgc.stop();
   BANI_CUDA(cudaGetLastError());
   BANI_CUDA(cudaStreamSynchronize(st));
   return ix.release();

@@ -445,6 +445,7 @@ void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_
       for (int attempt = 0; attempt < 2; attempt++) {
         if (cap > 0xfffffff0ull) fail(BANI_ERR_LIMIT, "query chunk produces more than 2^32 minimizers");
         fragHash.alloc(std::max<uint64_t>(cap, 1), st);
+        Stage sg(ctx, "q_sketch", (double)F * fragLen / 4.0);
         T = sketch_sequences(ctx, d_desc.p, F, flen.data(), fragHash.p, nullptr, nullptr, cap, segStart.p);
         if (T <= cap) break;
         cap = T;
@@ -453,7 +454,8 @@ void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_
       // ---- B: sorted unique hashes per fragment
       DevBuf<int32_t> sCount(F, st); DevBuf<int> d_flags(2, st);
       BANI_CUDA(cudaMemsetAsync(d_flags.p, 0, 8, st));
-      sort_unique_kernel<<<F, SU_THREADS, 0, st>>>(fragHash.p, segStart.p, F, sCount.p, d_flags.p, d_flags.p + 1);
+      { Stage sg(ctx, "q_sort_unique", 8.0 * T);
+        sort_unique_kernel<<<F, SU_THREADS, 0, st>>>(fragHash.p, segStart.p, F, sCount.p, d_flags.p, d_flags.p + 1); ctx->launches++; }
       int hflags[2];
       BANI_CUDA(cudaMemcpyAsync(hflags, d_flags.p, 8, cudaMemcpyDeviceToHost, st));
       BANI_CUDA(cudaStreamSynchronize(st));
@@ -465,9 +467,11 @@ void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_
         // ---- C: lookup
         DevBuf<uint32_t> hitLo(T + 1, st), hitCnt(T + 1, st);
         DevBuf<unsigned long long> hitOff(T + 1, st);
-        lookup_kernel<<<nblk(T + 1), 256, 0, st>>>(fragHash.p, segStart.p, sCount.p, F, (uint32_t)T, ix->ukeys.p, ix->uoff.p,
-                                                 ix->dir.p, ix->dirBits, hitLo.p, hitCnt.p);
-        { size_t tb = cub_scan_u64_temp(T + 1); DevBuf<uint8_t> tmp(tb, st);
+        { Stage sg(ctx, "lookup", 12.0 * T);
+          lookup_kernel<<<nblk(T + 1), 256, 0, st>>>(fragHash.p, segStart.p, sCount.p, F, (uint32_t)T, ix->ukeys.p, ix->uoff.p,
+                                                   ix->dir.p, ix->dirBits, hitLo.p, hitCnt.p);
+          ctx->launches++;
+          size_t tb = cub_scan_u64_temp(T + 1); DevBuf<uint8_t> tmp(tb, st);
           cub_exclusive_sum_u32_to_u64(tmp.p, tb, hitCnt.p, (uint64_t *)hitOff.p, T + 1, st); }
         unsigned long long N = 0;
         BANI_CUDA(cudaMemcpyAsync(&N, hitOff.p + T, 8, cudaMemcpyDeviceToHost, st));
@@ -480,9 +484,11 @@ void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_
         if (N > 0) {
           // ---- D: gather + sort
           DevBuf<unsigned long long> keysA(N, st), keysB(N, st);
-          gather_kernel<<<nblk(T), 256, 0, st>>>(segStart.p, F, (uint32_t)T, hitLo.p, hitCnt.p, hitOff.p, ix->posIdx.p, keysA.p);
+          { Stage sg(ctx, "hit_gather", 12.0 * N);
+            gather_kernel<<<nblk(T), 256, 0, st>>>(segStart.p, F, (uint32_t)T, hitLo.p, hitCnt.p, hitOff.p, ix->posIdx.p, keysA.p); ctx->launches++; }
           int fbits = 1; while ((1ll << fbits) < F) fbits++;
-          { size_t tb = cub_sort_keys_u64_temp(N); DevBuf<uint8_t> tmp(tb, st);
+          { Stage sg(ctx, "hit_sort", 16.0 * N);
+            size_t tb = cub_sort_keys_u64_temp(N); DevBuf<uint8_t> tmp(tb, st);
             cub_sort_keys_u64(tmp.p, tb, (const uint64_t *)keysA.p, (uint64_t *)keysB.p, N, 0, 32 + fbits, st); }
           keysA.release();
 
@@ -490,8 +496,10 @@ void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_
           L1Args la; la.keys = keysB.p; la.N = N; la.segStart = segStart.p; la.hitOff = hitOff.p; la.sCount = sCount.p;
           la.minHits = ctx->d_minHits.p; la.recSeq = ix->seqId.p; la.recWpos = ix->wpos.p; la.fragLen = fragLen;
           DevBuf<uint32_t> head(N + 1, st), headScan(N + 1, st);
-          l1_flag_kernel<<<nblk(N + 1), 256, 0, st>>>(la, head.p);
-          { size_t tb = cub_scan_u32_temp(N + 1); DevBuf<uint8_t> tmp(tb, st);
+          { Stage sg(ctx, "l1_flags", 8.0 * N);
+            l1_flag_kernel<<<nblk(N + 1), 256, 0, st>>>(la, head.p);
+            ctx->launches++;
+            size_t tb = cub_scan_u32_temp(N + 1); DevBuf<uint8_t> tmp(tb, st);
             cub_exclusive_sum_u32(tmp.p, tb, head.p, headScan.p, N + 1, st); }
           uint32_t C = 0;
           BANI_CUDA(cudaMemcpyAsync(&C, headScan.p + N, 4, cudaMemcpyDeviceToHost, st));
@@ -500,7 +508,8 @@ void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_
 
           if (C > 0) {
             DevBuf<int32_t> cFrag(C, st), cSeq(C, st), cStart(C, st), cEnd(C, st), cPos(C, st), cBest(C, st);
-            l1_write_kernel<<<nblk(N), 256, 0, st>>>(la, head.p, headScan.p, cFrag.p, cSeq.p, cStart.p, cEnd.p);
+            { Stage sg(ctx, "l1_write", 8.0 * N);
+              l1_write_kernel<<<nblk(N), 256, 0, st>>>(la, head.p, headScan.p, cFrag.p, cSeq.p, cStart.p, cEnd.p); ctx->launches++; }
             head.release(); headScan.release(); keysB.release();
 
             // ---- F: L2
@@ -514,7 +523,8 @@ void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_
             DevBuf<unsigned long long> d_n2(1, st);
             BANI_CUDA(cudaMemsetAsync(d_n2.p, 0, 8, st));
             l2.scratch = scratch.p; l2.cPos = cPos.p; l2.cBest = cBest.p; l2.ctr_n2 = d_n2.p;
-            l2_kernel<<<blocks, 64, 0, st>>>(l2);
+            { Stage sg(ctx, "l2");
+              l2_kernel<<<blocks, 64, 0, st>>>(l2); ctx->launches++; }
 
             // ---- G: report
             RepArgs ra; ra.cFrag = cFrag.p; ra.cSeq = cSeq.p; ra.cPos = cPos.p; ra.cBest = cBest.p; ra.C = C;
@@ -522,6 +532,7 @@ void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_
             ra.upper = ctx->d_upper.p; ra.pid = pid; ra.fragLen = fragLen;
             DevBuf<uint32_t> keep(C + 1, st), keepScan(C + 1, st);
             keep_flag_kernel<<<nblk(C + 1), 256, 0, st>>>(ra, keep.p);
+            ctx->launches++;
             { size_t tb = cub_scan_u32_temp(C + 1); DevBuf<uint8_t> tmp(tb, st);
               cub_exclusive_sum_u32(tmp.p, tb, keep.p, keepScan.p, C + 1, st); }
             uint32_t R = 0; unsigned long long n2 = 0;
@@ -531,7 +542,8 @@ void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_
             out.ctr.n2 += n2; out.ctr.mappings += R;
             if (R > 0) {
               DevBuf<bani_mapping> rows(R, st); DevBuf<int32_t> rFrag(R, st);
-              rows_kernel<<<nblk(C), 256, 0, st>>>(ra, keep.p, keepScan.p, rows.p, rFrag.p);
+              { Stage sg(ctx, "report", 44.0 * R);
+                rows_kernel<<<nblk(C), 256, 0, st>>>(ra, keep.p, keepScan.p, rows.p, rFrag.p); ctx->launches++; }
               if (wantRows) {
                 size_t old = out.rows.size(); out.rows.resize(old + R);
                 BANI_CUDA(cudaMemcpyAsync(out.rows.data() + old, rows.p, sizeof(bani_mapping) * (size_t)R, cudaMemcpyDeviceToHost, st));
@@ -548,10 +560,12 @@ void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_
                 CgiArgs ca; ca.rows = rows.p; ca.rFrag = rFrag.p; ca.R = R; ca.fragQuery = d_fragQuery.p;
                 ca.contigGenome = ix->contigGenome.p; ca.contigBinOff = ix->contigBinOff.p; ca.fragLen = fragLen;
                 ca.totalBins = ix->totalBins; ca.nGenomes = nG; ca.table = table.p; ca.touched = touched.p;
-                cgi_scatter_kernel<<<nblk(R), 256, 0, st>>>(ca);
                 DevBuf<int32_t> oCount((size_t)nQc * nG, st); DevBuf<float> oIdent((size_t)nQc * nG, st);
-                cgi_sum_kernel<<<nblk((uint64_t)nQc * nG), 256, 0, st>>>(table.p, touched.p, ix->contigBinOff.p, d_gce.p,
-                                                                        ix->totalBins, nG, nQc, oCount.p, oIdent.p);
+                { Stage sg(ctx, "cgi", 48.0 * R);
+                  cgi_scatter_kernel<<<nblk(R), 256, 0, st>>>(ca);
+                  ctx->launches++;
+                  cgi_sum_kernel<<<nblk((uint64_t)nQc * nG), 256, 0, st>>>(table.p, touched.p, ix->contigBinOff.p, d_gce.p,
+                                                                          ix->totalBins, nG, nQc, oCount.p, oIdent.p); ctx->launches++; }
                 BANI_CUDA(cudaMemcpyAsync(hCount.data(), oCount.p, 4 * (size_t)nQc * nG, cudaMemcpyDeviceToHost, st));
                 BANI_CUDA(cudaMemcpyAsync(hIdent.data(), oIdent.p, 4 * (size_t)nQc * nG, cudaMemcpyDeviceToHost, st));
                 BANI_CUDA(cudaStreamSynchronize(st));

@@ -170,7 +170,9 @@ void genome_create_batch(Ctx *ctx, int32_t nGenomes, const int32_t *genOff, cons
     int64_t base = off[c0];
     if (off[c1] - base != bytes) fail(BANI_ERR_ARG, "contig offsets must be contiguous and ascending");
     DevBuf<uint8_t> stage((size_t)bytes + 64, st);
-    if (bytes) BANI_CUDA(cudaMemcpyAsync(stage.p, seq + base, (size_t)bytes, cudaMemcpyHostToDevice, st));
+    { Stage sg(ctx, "h2d_ascii", (double)bytes);
+      if (bytes) BANI_CUDA(cudaMemcpyAsync(stage.p, seq + base, (size_t)bytes, cudaMemcpyHostToDevice, st)); }
+    Stage sgp(ctx, "pack", 1.25 * (double)bytes);
     BANI_CUDA(cudaMemsetAsync(stage.p + bytes, 'A', 64, st));
     std::vector<PackContig> pc(nC);
     uint64_t tiles = 0;
@@ -203,12 +205,14 @@ void genome_create_batch(Ctx *ctx, int32_t nGenomes, const int32_t *genOff, cons
       DevBuf<uint32_t> tileExc(tiles + 1, st), tileExcOff(tiles + 1, st);
       BANI_CUDA(cudaMemsetAsync(tileExc.p + tiles, 0, 4, st));
       pack_kernel<<<(unsigned)tiles, PACK_THREADS, 0, st>>>(stage.p, d_pc.p, nC, tileExc.p);
+      ctx->launches++;
       BANI_CUDA(cudaGetLastError());
       size_t tb = cub_scan_u32_temp(tiles + 1);
       DevBuf<uint8_t> tmp(tb, st);
       cub_exclusive_sum_u32(tmp.p, tb, tileExc.p, tileExcOff.p, tiles + 1, st);
       DevBuf<uint32_t> d_cexc(nC + 1, st);
       gather_contig_exc<<<(nC + 1 + 255) / 256, 256, 0, st>>>(d_pc.p, nC, tileExcOff.p, (uint32_t)tiles, d_cexc.p);
+      ctx->launches++;
       std::vector<uint32_t> cexc(nC + 1);
       BANI_CUDA(cudaMemcpyAsync(cexc.data(), d_cexc.p, 4 * (nC + 1), cudaMemcpyDeviceToHost, st));
       BANI_CUDA(cudaStreamSynchronize(st));
@@ -231,6 +235,7 @@ void genome_create_batch(Ctx *ctx, int32_t nGenomes, const int32_t *genOff, cons
         }
         BANI_CUDA(cudaMemcpyAsync(d_pc.p, pc.data(), sizeof(PackContig) * nC, cudaMemcpyHostToDevice, st));
         pack_exc_kernel<<<(unsigned)tiles, PACK_THREADS, 0, st>>>(stage.p, d_pc.p, nC, tileExc.p, tileExcOff.p);
+        ctx->launches++;
         BANI_CUDA(cudaGetLastError());
       }
       BANI_CUDA(cudaStreamSynchronize(st));   // pc / staging go out of scope
@@ -263,7 +268,9 @@ void genome_decode(Ctx *ctx, const Genome *g, int32_t contig, uint8_t *out, int6
   DevBuf<uint8_t> d(L, st);
   int nExc = (int)(g->excOff[contig + 1] - g->excOff[contig]);
   decode_kernel<<<(L + 255) / 256, 256, 0, st>>>(g->packed.p + g->wordOff[contig], nullptr, nullptr, 0, L, d.p);
+  ctx->launches++;
   if (nExc) decode_patch_kernel<<<(nExc + 255) / 256, 256, 0, st>>>(g->excPos.p + g->excOff[contig], g->excByte.p + g->excOff[contig], nExc, d.p);
+  ctx->launches++;
   BANI_CUDA(cudaGetLastError());
   BANI_CUDA(cudaMemcpyAsync(out, d.p, L, cudaMemcpyDeviceToHost, st));
   BANI_CUDA(cudaStreamSynchronize(st));

@@ -31,7 +31,7 @@ namespace bani {
 static constexpr int SK_THREADS = 256;
 static constexpr int SK_P = 16;                       // positions per thread
 static constexpr int SK_SLOTS = SK_THREADS * SK_P;    // 4096 hash slots per CTA = halo + tile
-static constexpr int SK_WMAX = 256;
+static constexpr int SK_WMAX = 1024;
 static constexpr int SK_KMAX = 32;
 static constexpr int SK_ASCII = SK_SLOTS + SK_KMAX + 64;   // bytes staged per CTA (16-aligned start + slack)
 
@@ -375,6 +375,7 @@ uint64_t sketch_sequences(Ctx *ctx, const SeqDesc *d_desc, int32_t nSeq, const i
   if (k == 16) launch_sketch<16>(a, st);
   else if (k == 21) launch_sketch<21>(a, st);
   else launch_sketch<0>(a, st);
+  ctx->launches++;
   BANI_CUDA(cudaGetLastError());
   unsigned long long total = 0;
   BANI_CUDA(cudaMemcpyAsync(&total, state.p + tiles, 8, cudaMemcpyDeviceToHost, st));

@@ -33,6 +33,7 @@ void synth_genome(Ctx *ctx, uint64_t seed, uint32_t ancestor, uint32_t strain, u
   cudaStream_t st = ctx->stream;
   DevBuf<uint8_t> d((size_t)len, st);
   synth_kernel<<<(unsigned)((len + 255) / 256), 256, 0, st>>>(seed, ancestor, strain, ppm, len, d.p);
+  ctx->launches++;
   BANI_CUDA(cudaGetLastError());
   BANI_CUDA(cudaMemcpyAsync(hostOut, d.p, (size_t)len, cudaMemcpyDeviceToHost, st));
   BANI_CUDA(cudaStreamSynchronize(st));

@@ -1,0 +1,62 @@
+"""Multi-GPU layout of a many-to-many run: one process per GPU, references sharded round-robin.
+
+This is exactly the reference's threading rule lifted to GPUs (src/cgi/include/
+computeCoreIdentity.hpp:457-487): shard g owns references j with j % G == g, every shard maps
+ALL queries against its own index, results of different shards are disjoint, and a local
+reference id becomes global as local * G + g.  The only exchange is the final gather of the
+dense per-pair tables (count int32, identity float32); no data-path collective exists.
+"""
+import numpy as np
+
+
+def shard_refs(n_refs, world, rank):
+    """splitReferenceGenomes (computeCoreIdentity.hpp:457-474): indices of the references of shard `rank`."""
+    return list(range(rank, n_refs, world))
+
+
+def global_ref_id(local_id, world, rank):
+    """correctRefGenomeIds (computeCoreIdentity.hpp:480-487)."""
+    return local_id * world + rank
+
+
+def dense_tables(cgi_results, n_queries, n_local_refs):
+    """CGI result rows of one shard -> dense [n_queries, n_local_refs] (count, identity) tables."""
+    cnt = np.zeros((n_queries, max(n_local_refs, 0)), np.int32)
+    idn = np.zeros((n_queries, max(n_local_refs, 0)), np.float32)
+    if len(cgi_results):
+        q = cgi_results["qryGenomeId"]; r = cgi_results["refGenomeId"]
+        cnt[q, r] = cgi_results["countSeq"]
+        idn[q, r] = cgi_results["identity"]
+    return cnt, idn
+
+
+def merge_shards(tables, n_queries, n_refs, world):
+    """tables[g] = (count, identity) of shard g, shapes [n_queries, len(shard_refs(n_refs, world, g))].
+    Returns the global [n_queries, n_refs] tables."""
+    cnt = np.zeros((n_queries, n_refs), np.int32)
+    idn = np.zeros((n_queries, n_refs), np.float32)
+    for g, (c, i) in enumerate(tables):
+        cols = shard_refs(n_refs, world, g)
+        if cols:
+            cnt[:, cols] = c[:, :len(cols)]
+            idn[:, cols] = i[:, :len(cols)]
+    return cnt, idn
+
+
+def gather_tables(cnt_local, idn_local, n_refs, world, rank, dist=None, device=None):
+    """All-gather of the per-shard tables over torch.distributed (NCCL on GPUs, gloo on CPU).
+    Shards are padded to the largest shard so that one collective per table suffices."""
+    n_queries = cnt_local.shape[0]
+    if world == 1 or dist is None:
+        return merge_shards([(cnt_local, idn_local)], n_queries, n_refs, 1)
+    import torch
+    width = (n_refs + world - 1) // world
+    pc = np.zeros((n_queries, width), np.int32); pi = np.zeros((n_queries, width), np.float32)
+    pc[:, :cnt_local.shape[1]] = cnt_local; pi[:, :idn_local.shape[1]] = idn_local
+    tc = torch.from_numpy(pc); ti = torch.from_numpy(pi)
+    if device is not None:
+        tc = tc.to(device); ti = ti.to(device)
+    gc = [torch.empty_like(tc) for _ in range(world)]; gi = [torch.empty_like(ti) for _ in range(world)]
+    dist.all_gather(gc, tc); dist.all_gather(gi, ti)
+    tables = [(gc[g].cpu().numpy(), gi[g].cpu().numpy()) for g in range(world)]
+    return merge_shards(tables, n_queries, n_refs, world)

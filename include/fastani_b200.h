@@ -110,6 +110,17 @@ BANI_API int  bani_ctx_sync(bani_ctx *ctx);
 /* Raw CUDA stream (cudaStream_t) every launch of this context goes to; for event timing. */
 BANI_API void *bani_ctx_stream(bani_ctx *ctx);
 
+/* Per-stage device timing.  When enabled, every stage of HP1/HP2 is bracketed by CUDA events on
+ * the context's stream; bani_ctx_profile_read() synchronises, sums the elapsed time, launch count and
+ * algorithmic bytes per stage name since the last read, and clears the record.  names: n_max
+ * buffers of 32 chars. */
+BANI_API int  bani_ctx_profile_enable(bani_ctx *ctx, int on);
+BANI_API int  bani_ctx_profile_read(bani_ctx *ctx, char (*names)[32], double *ms, double *algo_bytes,
+                                    int32_t *launches, int32_t n_max, int32_t *n);
+
+/* Number of this library's own kernels launched on the context so far (CUB launches excluded). */
+BANI_API uint64_t bani_ctx_launch_count(const bani_ctx *ctx);
+
 /* Pinned host memory for staging genomes (optional; pageable buffers also work). */
 BANI_API int  bani_host_alloc(size_t bytes, void **out);
 BANI_API void bani_host_free(void *p);

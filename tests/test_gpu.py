@@ -1,0 +1,224 @@
+"""GPU (-m gpu): parity of the CUDA path, through the C ABI, against the oracle and the golden fixtures."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import fastani_b200 as fb
+import pyoracle as po
+from conftest import GOLDEN
+from fastani_b200 import parallel
+from fastani_b200.synth import synth_genome
+
+pytestmark = pytest.mark.gpu
+
+EC = os.path.join(GOLDEN, "Escherichia_coli_str_K12_MG1655.fna.gz")
+SH = os.path.join(GOLDEN, "Shigella_flexneri_2a_01.fna.gz")
+
+
+@pytest.fixture(scope="module")
+def real():
+    return fb.read_fasta(EC), fb.read_fasta(SH)
+
+
+@pytest.fixture(scope="module")
+def edge():
+    return fb.read_fasta(os.path.join(GOLDEN, "edge_mixed.fa"))
+
+
+def test_pack_roundtrip_and_exceptions(edge):
+    ctx = fb.Context(fb.Parameters())
+    g = ctx.genome(edge)
+    nexc = 0
+    for c, (_, sq) in enumerate(edge):
+        want = po.upper(sq)
+        assert (g.decode(c) == want).all()
+        nexc += int(np.isin(want, np.frombuffer(b"ACGT", np.uint8), invert=True).sum())
+    inf = g.info()
+    assert inf["n_exceptions"] == nexc and inf["n_contigs"] == 16
+    empty = ctx.genome([])
+    assert empty.info()["n_contigs"] == 0
+
+
+@pytest.mark.parametrize("k,w", [(16, 24), (21, 15), (16, 13), (16, 40), (11, 5), (32, 3), (7, 1), (24, 64)])
+def test_sketch_edge_cases_vs_reference_golden(edge, k, w):
+    ctx = fb.Context(fb.Parameters(kmerSize=k, windowSize=w))
+    sk = fb.Sketch(ctx, [ctx.genome(edge)])
+    want = np.fromfile(os.path.join(GOLDEN, "edge_mixed.k%dw%d.mi" % (k, w)), dtype=fb.MINIMIZER_DTYPE)
+    got = sk.minimizerIndex()
+    assert len(got) == len(want) and (got == want).all()
+    assert sk.stats()["n_unique"] == len(np.unique(want["hash"]))
+    assert sk.sequencesByFileInfo == [16]
+
+
+def test_sketch_real_genomes_sha(real):
+    sums = json.load(open(os.path.join(GOLDEN, "sketch_sha256.json")))
+    for tag, gen in zip(("ecoli", "shigella"), real):
+        for k, w in [(16, 24), (21, 15)]:
+            ctx = fb.Context(fb.Parameters(kmerSize=k, windowSize=w))
+            sk = fb.Sketch(ctx, [ctx.genome(gen)])
+            got = sk.minimizerIndex()
+            s = sums["%s.k%dw%d" % (tag, k, w)]
+            assert len(got) == s["records"] and hashlib.sha256(got.tobytes()).hexdigest() == s["sha256"]
+            if tag == "ecoli" and k == 16:
+                assert sk.stats()["n_unique"] == 361568
+                h = int(got["hash"][1000])
+                hits, n = sk.lookup(h)
+                assert hits == [(int(r["seqId"]), int(r["wpos"])) for r in got[got["hash"] == h]]
+                assert sk.lookup(12345)[1] == int((got["hash"] == 12345).sum())
+
+
+def test_empty_and_degenerate_inputs():
+    ctx = fb.Context(fb.Parameters())
+    sk = fb.Sketch(ctx, [])                                   # a shard without references
+    q = ctx.genome([("q", synth_genome(1, 1, 0, 0, 20000).tobytes())])
+    m = fb.Map(ctx, sk, q)
+    assert len(m.rows) == 0 and m.totalQueryFragments == 6
+    res, tot, _ = fb.compute_cgi(ctx, sk, [q])
+    assert len(res) == 0 and int(tot[0]) == 6
+    # all-N and too-short queries against a real index
+    sk2 = fb.Sketch(ctx, [q])
+    for seq, frags in ((b"N" * 9000, 3), (b"ACGT" * 100, 0), (b"", 0)):
+        m = fb.Map(ctx, sk2, ctx.genome([("x", seq)]))
+        assert len(m.rows) == 0 and m.totalQueryFragments == frags
+    assert fb.Map(ctx, sk2, ctx.genome([])).totalQueryFragments == 0
+
+
+def test_map_real_pair_rows_counters_cgi(real):
+    ec, sh = real
+    ctx = fb.Context(fb.Parameters())
+    ge, gs = ctx.genomes([ec, sh])
+    sk = fb.Sketch(ctx, [ge])
+    m = fb.Map(ctx, sk, gs)
+    want = np.fromfile(os.path.join(GOLDEN, "s2e.k16.map"), dtype=fb.MAPPING_DTYPE)
+    assert m.totalQueryFragments == 1608
+    assert m.rows.tobytes() == want.tobytes()                 # all 4138 records, every field, reference order
+    c = m.counters.as_dict()
+    assert (c["sum_s"], c["hits"], c["candidates"], c["n2"], c["mappings"]) == (381646, 311331, 5058, 2815830, 4138)
+    res, tot, _ = fb.compute_cgi(ctx, sk, [gs])
+    assert [(int(r["refGenomeId"]), int(r["countSeq"]), "%g" % r["identity"]) for r in res] == [(0, 1303, "97.7507")]
+    # callback form of skch::Map
+    seen = []
+    fb.Map(ctx, sk, gs, f=lambda r: seen.append(int(r["querySeqId"])))
+    assert len(seen) == 4138 and seen == sorted(seen)
+
+
+def test_two_refs_two_queries_against_oracle(real):
+    ec, sh = real
+    ctx = fb.Context(fb.Parameters())
+    ge, gs = ctx.genomes([ec, sh])
+    sk = fb.Sketch(ctx, [ge, gs])
+    assert sk.sequencesByFileInfo == [1, 3]
+    rec, sbf, _ = po.sketch_genomes([ec, sh], 16, 24)
+    ix = po.Index(rec)
+    exp = []
+    for qi, (q, gq) in enumerate(((sh, gs), (ec, ge))):
+        rows, tq, _ = po.map_genome(ix, q, 16, 24, 3000)
+        assert fb.Map(ctx, sk, gq).rows.tobytes() == rows.tobytes()
+        exp += [(qi, g, c, np.float32(i), tq) for g, c, i in po.cgi(rows, sbf, 3000)]
+    res, tot, _ = fb.compute_cgi(ctx, sk, [gs, ge])
+    got = [(int(r["qryGenomeId"]), int(r["refGenomeId"]), int(r["countSeq"]), np.float32(r["identity"]),
+            int(r["totalQueryFragments"])) for r in res]
+    assert got == exp
+    assert ["%g" % r["identity"] for r in res] == ["97.7507", "100", "100", "97.664"]     # README.md:80, fastani_tests.cpp:61
+
+
+@pytest.mark.parametrize("k,L", [(16, 1000), (16, 5000), (21, 3000), (21, 5000), (21, 1000)])
+def test_parameter_sweep_vs_reference(real, k, L):
+    ec, sh = real
+    sums = json.load(open(os.path.join(GOLDEN, "map_sha256.json")))
+    ctx = fb.Context(fb.Parameters(kmerSize=k, minReadLength=L))
+    ge, gs = ctx.genomes([ec, sh])
+    m = fb.Map(ctx, fb.Sketch(ctx, [ge]), gs)
+    if (k, L) == (21, 1000):
+        assert ctx.windowSize == 1000 and len(m.rows) == 0
+        return
+    s = sums["s2e.k%d.L%d" % (k, L)]
+    assert len(m.rows) == s["records"] and hashlib.sha256(m.rows.tobytes()).hexdigest() == s["sha256"]
+
+
+def _cluster_set(n_clusters, n_strains, L, seed=7):
+    gs = []
+    for c in range(n_clusters):
+        for s in range(n_strains):
+            seq = synth_genome(seed, c + 1, s, 6000 * s, L)
+            if s == 2:                      # one multi-contig strain per cluster, with an N gap and lower case
+                a = seq.tobytes()
+                gs.append([("c%ds%d_a" % (c, s), a[:L // 3].lower()), ("c%ds%d_tiny" % (c, s), a[L // 3:L // 3 + 500]),
+                           ("c%ds%d_b" % (c, s), a[L // 3 + 500:L // 2] + b"N" * 700 + a[L // 2:])])
+            else:
+                gs.append([("c%ds%d" % (c, s), seq.tobytes())])
+    return gs
+
+
+def test_many_to_many_synthetic_vs_oracle_and_shard_invariance():
+    """12 x 12 synthetic clusters: every CGI row equals the oracle's; mapping in 3 shards and merging
+    (the multi-GPU rule) equals the single-shard result; self pairs are 100 % over all fragments."""
+    L = 90000
+    genomes = _cluster_set(3, 4, L)
+    ctx = fb.Context(fb.Parameters())
+    hs = ctx.genomes(genomes)
+    n = len(hs)
+    sk = fb.Sketch(ctx, hs)
+    res, tot, ctr = fb.compute_cgi(ctx, sk, hs)
+    cnt, idn = parallel.dense_tables(res, n, n)
+    # oracle
+    rec, sbf, _ = po.sketch_genomes(genomes, 16, 24)
+    ix = po.Index(rec)
+    assert (sk.minimizerIndex() == rec).all()
+    ocnt = np.zeros((n, n), np.int32); oidn = np.zeros((n, n), np.float32)
+    for qi, q in enumerate(genomes):
+        rows, tq, _ = po.map_genome(ix, q, 16, 24, 3000)
+        assert tq == int(tot[qi])
+        if qi % 5 == 0:
+            assert fb.Map(ctx, sk, hs[qi]).rows.tobytes() == rows.tobytes()
+        for g, c, i in po.cgi(rows, sbf, 3000):
+            ocnt[qi, g] = c; oidn[qi, g] = i
+    assert (cnt == ocnt).all()
+    assert (idn.view(np.uint32) == oidn.view(np.uint32)).all()
+    for i in range(n):
+        assert cnt[i, i] == tot[i] and idn[i, i] == 100.0
+    assert int((cnt > 0).sum()) >= 3 * 16
+    # shard invariance
+    G = 3
+    tabs = []
+    for g in range(G):
+        ids = parallel.shard_refs(n, G, g)
+        r, _, _ = fb.compute_cgi(ctx, fb.Sketch(ctx, [hs[i] for i in ids]), hs)
+        tabs.append(parallel.dense_tables(r, n, len(ids)))
+    mc, mi = parallel.merge_shards(tabs, n, n, G)
+    assert (mc == cnt).all() and (mi.view(np.uint32) == idn.view(np.uint32)).all()
+
+
+def test_full_size_properties():
+    """Size-independent properties at BASELINE genome size (5 Mbp): sketch ordering / density, index
+    consistency, self-mapping = 100 % for every fragment, strain pair close to its simulated divergence."""
+    L = 5_000_000
+    ctx = fb.Context(fb.Parameters())
+    a = ctx.synth_genome(3, 1, 0, 0, L); b = ctx.synth_genome(3, 1, 4, 24000, L)
+    ga, gb = ctx.genomes([[("a", a)], [("b", b)]])
+    sk = fb.Sketch(ctx, [ga, gb])
+    rec = sk.minimizerIndex()
+    st = sk.stats()
+    key = rec["seqId"].astype(np.int64) << 32 | rec["wpos"].astype(np.int64)
+    assert (np.diff(key) > 0).all()                                    # ordered, (seqId, wpos) unique
+    assert abs(len(rec) / (2 * L) - 2 / 25) < 0.002                    # density 2/(w+1)
+    assert st["n_unique"] == len(np.unique(rec["hash"]))
+    res, tot, _ = fb.compute_cgi(ctx, sk, [ga, gb])
+    cnt, idn = parallel.dense_tables(res, 2, 2)
+    assert int(tot[0]) == L // 3000 and cnt[0, 0] == tot[0] and cnt[1, 1] == tot[1]
+    assert idn[0, 0] == 100.0 and idn[1, 1] == 100.0
+    assert cnt[0, 1] > 0.95 * tot[0] and abs(float(idn[0, 1]) - 97.6) < 0.5
+
+
+def test_device_synth_matches_numpy_twin():
+    ctx = fb.Context(fb.Parameters())
+    for a, s, ppm, n in [(0, 0, 0, 10000), (3, 5, 30000, 100001), (7, 19, 114000, 5000)]:
+        assert (ctx.synth_genome(3, a, s, ppm, n) == synth_genome(3, a, s, ppm, n)).all()
+
+
+def test_smoke_entry():
+    import __graft_entry__ as g
+    g.smoke()

@@ -1,0 +1,119 @@
+"""CPU: host logic of the product and the C-ABI surface (no compute calls without a GPU)."""
+import ctypes as C
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+import fastani_b200 as fb
+from conftest import GOLDEN, ROOT
+from fastani_b200 import api, parallel, report
+from fastani_b200.synth import synth_genome
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "fastani_b200.h")).read()
+    declared = set(re.findall(r"BANI_API\s+[\w\s\*]*?\b(bani_\w+)\s*\(", hdr))
+    assert len(declared) >= 28
+    lib = C.CDLL(fb.library_path())
+    for name in declared:
+        assert hasattr(lib, name), "libfastani_b200.so does not export %s" % name
+    assert declared == set(api.EXPORTED_SYMBOLS)
+    fb.load_library()
+
+
+def test_no_cpu_fallback():
+    """The product must fail loudly without a GPU, never route through a CPU path."""
+    if _has_gpu():
+        pytest.skip("GPU present")
+    with pytest.raises(fb.BaniError) as e:
+        fb.Context(fb.Parameters())
+    assert e.value.code == -2 and "no CPU fallback" in str(e.value)
+
+
+def test_product_never_imports_the_oracle():
+    for root, _, files in os.walk(os.path.join(ROOT, "fastani_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(root, f), errors="ignore").read()
+                assert "pyoracle" not in src and "liboracle" not in src and "ani_oracle" not in src, f
+
+
+def test_recommended_window_size():
+    ws = json.load(open(os.path.join(GOLDEN, "wsize.json")))
+    for key, want in ws.items():
+        k, L = map(int, key.split(","))
+        assert fb.Parameters(kmerSize=k, minReadLength=L).recommendedWindowSize() == want, key
+
+
+@pytest.mark.parametrize("s,k", [(243, 16), (100, 16), (258, 16), (1, 16), (17, 21), (300, 21), (64, 16)])
+def test_statistic_tables_bit_exact(s, k):
+    """The (s, shared) -> identity / upper-bound table the kernels index, against the reference."""
+    L = fb.load_library()
+    lines = open(os.path.join(GOLDEN, "stats_s%d_k%d.txt" % (s, k))).read().split("\n")
+    assert L.bani_stat_min_hits_relaxed(s, k, 80.0) == int(lines[0])
+    for x in range(s + 1):
+        a, b = C.c_float(), C.c_float()
+        assert L.bani_stat_identity(x, s, k, C.byref(a), C.byref(b)) == 0
+        _, ia, ib = lines[1 + x].split()
+        assert np.float32(a.value).view(np.uint32) == int(ia)
+        assert np.float32(b.value).view(np.uint32) == int(ib)
+
+
+def test_argument_errors():
+    L = fb.load_library()
+    a, b = C.c_float(), C.c_float()
+    assert L.bani_stat_identity(5, 3, 16, C.byref(a), C.byref(b)) == -1
+    assert b"bad arguments" in L.bani_last_error()
+    assert L.bani_ctx_sync(None) == -1
+
+
+def test_fasta_reader(tmp_path):
+    p = tmp_path / "x.fa"
+    p.write_bytes(b">c1 desc\r\nACGT\r\nacgtn\r\n\r\n>c2\nTT TT\n@fq1\nACGTAC\n+\nIIIIII\n@fq2 x\nGG\n+\n@I\n")
+    assert fb.read_fasta(str(p)) == [("c1", b"ACGTacgtn"), ("c2", b"TTTT"), ("fq1", b"ACGTAC"), ("fq2", b"GG")]
+    import gzip
+    gz = tmp_path / "x.fa.gz"
+    gz.write_bytes(gzip.compress(p.read_bytes()))
+    assert fb.read_fasta(str(gz)) == fb.read_fasta(str(p))
+    ec = fb.read_fasta(os.path.join(GOLDEN, "Escherichia_coli_str_K12_MG1655.fna.gz"))
+    assert [(n, len(s)) for n, s in ec] == [("NC_000913.3", 4641652)]
+
+
+def test_synth_is_deterministic_and_diverges_as_asked():
+    a = synth_genome(3, 1, 0, 0, 50000)
+    assert (a == synth_genome(3, 1, 0, 0, 50000)).all()
+    assert set(np.unique(a)) == set(b"ACGT")
+    b = synth_genome(3, 1, 5, 30000, 50000)
+    assert abs(float((a != b).mean()) - 0.03) < 0.004
+    assert float((a != synth_genome(3, 2, 0, 0, 50000)).mean()) > 0.7
+
+
+def test_sharding_rule_matches_reference():
+    # splitReferenceGenomes / correctRefGenomeIds (computeCoreIdentity.hpp:457-487)
+    for n, G in [(10, 3), (2, 8), (1000, 8), (0, 2)]:
+        seen = []
+        for g in range(G):
+            idx = parallel.shard_refs(n, G, g)
+            assert idx == [j for j in range(n) if j % G == g]
+            assert [parallel.global_ref_id(l, G, g) for l in range(len(idx))] == idx
+            seen += idx
+        assert sorted(seen) == list(range(n))
+
+
+def test_output_filter_and_format():
+    # sharedLength >= minGenomeLength * minFraction, float compare (computeCoreIdentity.hpp:326-332)
+    rows = [(0, 0, 10, 100, np.float32(97.75071)), (0, 1, 1, 100, np.float32(99.5)), (1, 0, 20, 50, np.float32(80.0))]
+    out = report.output_lines(rows, ["q0", "q1"], ["r0", "r1"], [150000, 150000], [150000, 90000], 3000, 0.2)
+    assert out == ["q0\tr0\t97.7507\t10\t100", "q1\tr0\t80\t20\t50"]
+    assert report.genome_length([2999, 3000, 7000], 3000) == 9000
