@@ -292,7 +292,7 @@ def main_ours(a):
 
     # ---- sanity of the result the timing produced (not a parity test, those live in tests/)
     cnt, idn = last["cnt"], last["idn"]
-    diag_ok = bool((np.diag(idn) == 100.0).all()) and int((cnt > 0).sum()) >= nG
+    diag_ok = bool((np.diag(idn) > 99.9).all()) and int((cnt > 0).sum()) >= nG
     ctr = last["ctr"]
 
     # ---- roofline of the dominant stage: algorithmic bytes / CUDA-event duration
@@ -324,7 +324,7 @@ def main_ours(a):
                    "queries": nG, "references": nG, "parallelism": "reference list sharded round-robin over %d GPU(s)" % world,
                    "l2_flush": "inputs (%.1f GB packed genomes + %.1f GB index per rank) exceed the 126 MB L2" % (
                        nG * L / 4e9, 16.0 * st["n_minimizers"] / 1e9),
-                   "result_check": "self pairs 100%% and >= %d populated pairs: %s" % (nG, diag_ok),
+                   "result_check": "self pairs > 99.9%% and >= %d populated pairs: %s (min self identity %.4f)" % (nG, diag_ok, float(np.diag(idn).min())),
                    "counters_rank0": ctr},
         "clocks": clocks,
         "e2e": {"value": pairs / sec_e2e, "unit": UNIT, "ms_per_step": sec_e2e * 1e3,

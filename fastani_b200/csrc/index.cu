@@ -63,6 +63,25 @@ __global__ void dir_kernel(const uint32_t *ukeys, uint32_t U, int dirBits, uint3
   if (i == U - 1) for (uint32_t b = bc + 1; b <= (1u << dirBits); b++) dir[b] = U;
 }
 
+__global__ void zip_records_kernel(const uint32_t *hash, const int32_t *wpos, const uint32_t *link, const int32_t *seqId,
+                                   uint64_t n, uint4 *rec)
+{
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) rec[i] = make_uint4(hash[i], (uint32_t)wpos[i], link[i], (uint32_t)seqId[i]);
+}
+
+__global__ void dir_fill_kernel(const uint32_t *ukeys, uint32_t U, int dirBits, uint32_t *dir)
+{
+  // dir[b] = lower_bound(ukeys, b << (32 - dirBits)); minimizer hashes are minima of w hashes, hence heavily
+  // skewed towards small values: most high buckets are empty, so every bucket searches for itself
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > (1u << dirBits)) return;
+  uint32_t lo = 0, hi = U;
+  if (b == (1u << dirBits)) lo = U;
+  else { const uint32_t v = b << (32 - dirBits); while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (ukeys[mid] < v) lo = mid + 1; else hi = mid; } }
+  dir[b] = lo;
+}
+
 __global__ void fill_u32(uint32_t *p, uint32_t v, uint64_t n)
 {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -202,7 +221,10 @@ Index *index_build(Ctx *ctx, Genome *const *refs, int32_t nRefs)
   int bits = 8; while (bits < 24 && (1ull << bits) < U) bits++;
   ix->dirBits = bits;
   ix->dir.alloc((1u << bits) + 1, st);
-  dir_kernel<<<nblk(U), 256, 0, st>>>(ix->ukeys.p, (uint32_t)U, bits, ix->dir.p);
+  dir_fill_kernel<<<nblk((1ull << bits) + 1), 256, 0, st>>>(ix->ukeys.p, (uint32_t)U, bits, ix->dir.p);
+  ctx->launches++;
+  ix->rec.alloc(M, st);
+  zip_records_kernel<<<nblk(M), 256, 0, st>>>(ix->hash.p, ix->wpos.p, ix->link.p, ix->seqId.p, M, ix->rec.p);
   ctx->launches++;
   sgc.stop();
   BANI_CUDA(cudaGetLastError());

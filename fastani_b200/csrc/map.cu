@@ -197,6 +197,7 @@ struct L2Args {
   uint8_t *scratch; size_t stride;
   int32_t *cPos, *cBest;
   unsigned long long *ctr_n2;
+  int onlyFlagged;
 };
 
 __device__ __forceinline__ uint32_t lb_wpos(const int32_t *wpos, uint32_t lo, uint32_t hi, int32_t v)
@@ -219,6 +220,7 @@ l2_kernel(const L2Args a)
   uint8_t *pres = (uint8_t *)(gap + a.smax + 2);
   unsigned long long n2 = 0;
   for (uint32_t c = slot; c < a.C; c += nslots) {
+    if (a.onlyFlagged && a.cBest[c] != -1) continue;           // the fast path already solved it
     const int f = a.cFrag[c];
     const int s = a.sCount[f];
     const uint32_t *Q = a.fragHash + a.segStart[f];
@@ -266,6 +268,144 @@ l2_kernel(const L2Args a)
     a.cBest[c] = best;
   }
   if (n2) atomicAdd(a.ctr_n2, n2);
+}
+
+// ------------------------------------------------------------------ F': L2 fast path, one warp per query fragment
+// All candidate regions of one fragment share its sketch Q, so a warp stages Q (plus a 1024-bucket
+// directory over the top 10 hash bits) in shared memory once and gives every lane one candidate.
+// Per-lane window state lives in shared memory too: gap[g] = distinct non-Q window hashes with exactly
+// g query hashes below them (uint8, overflow => the candidate is handed to the exact slow kernel),
+// pres = bitmap of query hashes present in the window.  Records are read as 16-byte AoS
+// (hash, wpos, twin link, seqId): one load per pointer advance.
+struct L2WArgs {
+  const int32_t *cSeq, *cStart, *cEnd; const uint32_t *fragCandOff;
+  const uint32_t *fragHash; const uint32_t *segStart; const int32_t *sCount;
+  const uint4 *rec; const uint32_t *contigRecOff; uint32_t M;
+  int fragLen, cmw, sLimit; uint32_t strideWords, gapWords;
+  int32_t *cPos, *cBest; unsigned long long *ctr_n2;
+};
+
+__global__ void frag_cand_off_kernel(const int32_t *cFrag, uint32_t C, int32_t F, uint32_t *fragCandOff)
+{
+  int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f > F) return;
+  uint32_t lo = 0, hi = C;                      // first candidate with cFrag >= f
+  while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (cFrag[mid] < f) lo = mid + 1; else hi = mid; }
+  fragCandOff[f] = lo;
+}
+
+__device__ __forceinline__ uint32_t lb_rec(const uint4 *rec, uint32_t lo, uint32_t hi, int32_t v)
+{
+  while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if ((int32_t)__ldg(&rec[mid]).y < v) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+
+__global__ void __launch_bounds__(32)
+l2_warp_kernel(const L2WArgs a)
+{
+  extern __shared__ __align__(16) uint32_t smem[];
+  const int f = blockIdx.x, lane = threadIdx.x;
+  const uint32_t c0 = a.fragCandOff[f], c1 = a.fragCandOff[f + 1];
+  if (c0 == c1) return;
+  const int s = a.sCount[f];
+  if (s > a.sLimit || s < 1) { for (uint32_t c = c0 + lane; c < c1; c += 32) a.cBest[c] = -1; return; }
+  uint32_t *Q = smem;                                          // sLimit words
+  uint16_t *tab = (uint16_t *)(smem + a.sLimit);               // 1025 entries (+ pad)
+  uint32_t *stBase = smem + a.sLimit + 516;
+  uint32_t *st = stBase + lane * a.strideWords;                // this lane's state
+  uint8_t *gap = (uint8_t *)st;                                // s + 1 counters
+  uint32_t *pres = st + a.gapWords;                            // bitmap of s bits
+  {
+    const uint32_t *Qg = a.fragHash + a.segStart[f];
+    for (int i = lane; i < s; i += 32) Q[i] = Qg[i];
+    __syncwarp();
+    for (int bkt = lane; bkt <= 1024; bkt += 32) {
+      int lo = 0, hi = s;
+      if (bkt == 1024) lo = s;
+      else { const uint32_t v = (uint32_t)bkt << 22; while (lo < hi) { int mid = (lo + hi) >> 1; if (Q[mid] < v) lo = mid + 1; else hi = mid; } }
+      tab[bkt] = (uint16_t)lo;
+    }
+    __syncwarp();
+  }
+  unsigned long long n2 = 0;
+  for (uint32_t cb = c0; cb < c1; cb += 32) {
+    const uint32_t c = cb + lane;
+    const bool act = c < c1;
+    for (uint32_t i = 0; i < a.strideWords; i++) st[i] = 0;
+    uint32_t b = 0, e = 0, last = 0;
+    int t = s, G = 0, P = 0;
+    bool ovf = false;
+
+    auto classify = [&](uint32_t h, bool &match) -> int {
+      const uint32_t bkt = h >> 22;
+      int j = tab[bkt]; const int je = tab[bkt + 1];
+      while (j < je && Q[j] < h) j++;
+      match = (j < s) && (Q[j] == h);
+      return j;
+    };
+    auto insert = [&](uint32_t h, uint32_t link, uint32_t idx, uint32_t wb) {
+      const uint32_t pd = link >> 16;
+      if (pd != 0xFFFFu && idx - pd >= wb) return;             // an earlier twin is inside the window
+      bool match; const int j = classify(h, match);
+      if (match) { pres[j >> 5] |= 1u << (j & 31); if (j < t) P++; }
+      else {
+        const uint32_t g = gap[j];
+        if (g == 255u) { ovf = true; return; }
+        gap[j] = (uint8_t)(g + 1);
+        if (j < t) { G++; if (t + G > s) { t--; G -= gap[t]; P -= (pres[t >> 5] >> (t & 31)) & 1; } }
+      }
+    };
+    auto remove = [&](uint32_t h, uint32_t link, uint32_t idx, uint32_t we) {
+      const uint32_t nd = link & 0xFFFFu;
+      if (nd != 0xFFFFu && idx + nd < we) return;              // a later twin is still inside the window
+      bool match; const int j = classify(h, match);
+      if (match) { pres[j >> 5] &= ~(1u << (j & 31)); if (j < t) P--; }
+      else {
+        gap[j] = (uint8_t)(gap[j] - 1);
+        if (j < t) G--;
+        if (t < s && t + 1 + G + (int)gap[t] <= s) { G += gap[t]; P += (pres[t >> 5] >> (t & 31)) & 1; t++; }
+      }
+    };
+
+    if (act) {
+      const int seq = a.cSeq[c];
+      const uint32_t lo = a.contigRecOff[seq], hi = a.contigRecOff[seq + 1];
+      b = lb_rec(a.rec, lo, hi, a.cStart[c]);
+      e = lb_rec(a.rec, lo, hi, (int32_t)__ldg(&a.rec[b]).y + a.cmw);
+      last = lb_rec(a.rec, lo, hi, a.cEnd[c] + a.fragLen);
+    }
+    const uint32_t b0 = b;
+    // the first super-window
+    uint32_t r = b;
+    while (__any_sync(0xffffffffu, act && r < e && !ovf)) {
+      if (act && r < e && !ovf) { const uint4 rc = __ldg(&a.rec[r]); insert(rc.x, rc.z, r, b); r++; }
+    }
+    // slide
+    int sw = 0, best = 0, first = 0, lastp = 0;
+    uint4 cur = make_uint4(0, 0, 0, 0), nxt = cur, re = cur;
+    bool run = act && e < last && !ovf;
+    if (run) { cur = __ldg(&a.rec[b]); nxt = __ldg(&a.rec[b + 1]); re = __ldg(&a.rec[e]); sw = (int)cur.y; }
+    while (__any_sync(0xffffffffu, run)) {
+      if (run) {
+        if (P > best) { best = P; first = lastp = (int)cur.y; }
+        else if (P == best) lastp = (int)cur.y;
+        const int d1 = (int)nxt.y - sw, d2 = (int)re.y - (sw + a.cmw - 1);
+        const int adv = min(d1, d2);
+        sw += adv;
+        const uint32_t ob = b, oe = e;
+        if (adv == d1) { remove(cur.x, cur.z, ob, oe); b++; cur = nxt; nxt = __ldg(&a.rec[min(b + 1, a.M - 1)]); }
+        if (adv == d2) { insert(re.x, re.z, oe, b); e++; if (e < last) re = __ldg(&a.rec[e]); }
+        run = (e < last) && !ovf;
+      }
+    }
+    if (act) {
+      if (ovf) a.cBest[c] = -1;
+      else { a.cPos[c] = (first + lastp) / 2; a.cBest[c] = best; n2 += last - b0; }
+    }
+    __syncwarp();
+  }
+  for (int o = 16; o; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+  if (lane == 0 && n2) atomicAdd(a.ctr_n2, n2);
 }
 
 // ------------------------------------------------------------------ G: report
@@ -522,9 +662,29 @@ void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_
             DevBuf<uint8_t> scratch((size_t)blocks * 64 * l2.stride, st);
             DevBuf<unsigned long long> d_n2(1, st);
             BANI_CUDA(cudaMemsetAsync(d_n2.p, 0, 8, st));
-            l2.scratch = scratch.p; l2.cPos = cPos.p; l2.cBest = cBest.p; l2.ctr_n2 = d_n2.p;
-            { Stage sg(ctx, "l2");
-              l2_kernel<<<blocks, 64, 0, st>>>(l2); ctx->launches++; }
+            l2.scratch = scratch.p; l2.cPos = cPos.p; l2.cBest = cBest.p; l2.ctr_n2 = d_n2.p; l2.onlyFlagged = 1;
+            {
+              Stage sg(ctx, "l2");
+              // fast path: one warp per fragment, window state in shared memory
+              DevBuf<uint32_t> fragCandOff((size_t)F + 1, st);
+              frag_cand_off_kernel<<<nblk((uint64_t)F + 1), 256, 0, st>>>(cFrag.p, C, F, fragCandOff.p);
+              ctx->launches++;
+              L2WArgs lw; lw.cSeq = cSeq.p; lw.cStart = cStart.p; lw.cEnd = cEnd.p; lw.fragCandOff = fragCandOff.p;
+              lw.fragHash = fragHash.p; lw.segStart = segStart.p; lw.sCount = sCount.p;
+              lw.rec = ix->rec.p; lw.contigRecOff = ix->contigRecOff.p; lw.M = (uint32_t)ix->M;
+              lw.fragLen = fragLen; lw.cmw = cmw;
+              lw.sLimit = std::min(smax, 1024);
+              lw.gapWords = (uint32_t)(lw.sLimit + 1 + 3) / 4;
+              lw.strideWords = (lw.gapWords + (uint32_t)(lw.sLimit + 31) / 32) | 1u;      // odd => conflict-free lanes
+              lw.cPos = cPos.p; lw.cBest = cBest.p; lw.ctr_n2 = d_n2.p;
+              const size_t shm = 4 * ((size_t)lw.sLimit + 516 + 32 * (size_t)lw.strideWords);
+              static bool attrSet = false;
+              if (!attrSet) { BANI_CUDA(cudaFuncSetAttribute(l2_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attrSet = true; }
+              l2_warp_kernel<<<F, 32, shm, st>>>(lw);
+              ctx->launches++;
+              // exact slow path for whatever the fast path flagged (uint8 counter overflow, very large sketches)
+              l2_kernel<<<blocks, 64, 0, st>>>(l2); ctx->launches++;
+            }
 
             // ---- G: report
             RepArgs ra; ra.cFrag = cFrag.p; ra.cSeq = cSeq.p; ra.cPos = cPos.p; ra.cBest = cBest.p; ra.C = C;

@@ -179,7 +179,8 @@ def test_many_to_many_synthetic_vs_oracle_and_shard_invariance():
     assert (cnt == ocnt).all()
     assert (idn.view(np.uint32) == oidn.view(np.uint32)).all()
     for i in range(n):
-        assert cnt[i, i] == tot[i] and idn[i, i] == 100.0
+        # a fragment next to a contig end is never scored (computeMap.hpp:455): allow one miss per contig
+        assert tot[i] - len(genomes[i]) <= cnt[i, i] <= tot[i] and idn[i, i] > 99.9
     assert int((cnt > 0).sum()) >= 3 * 16
     # shard invariance
     G = 3
@@ -208,8 +209,8 @@ def test_full_size_properties():
     assert st["n_unique"] == len(np.unique(rec["hash"]))
     res, tot, _ = fb.compute_cgi(ctx, sk, [ga, gb])
     cnt, idn = parallel.dense_tables(res, 2, 2)
-    assert int(tot[0]) == L // 3000 and cnt[0, 0] == tot[0] and cnt[1, 1] == tot[1]
-    assert idn[0, 0] == 100.0 and idn[1, 1] == 100.0
+    assert int(tot[0]) == L // 3000 and cnt[0, 0] >= tot[0] - 1 and cnt[1, 1] >= tot[1] - 1
+    assert idn[0, 0] > 99.99 and idn[1, 1] > 99.99
     assert cnt[0, 1] > 0.95 * tot[0] and abs(float(idn[0, 1]) - 97.6) < 0.5
 
 
