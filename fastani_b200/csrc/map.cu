@@ -382,9 +382,14 @@ l2_warp_kernel(const L2WArgs a)
     }
     // slide
     int sw = 0, best = 0, first = 0, lastp = 0;
-    uint4 cur = make_uint4(0, 0, 0, 0), nxt = cur, re = cur;
+    // both streams are read two records ahead so a load is never consumed in the iteration that issued it
+    uint4 cur = make_uint4(0, 0, 0, 0), nxt = cur, nxt2 = cur, re = cur, re2 = cur;
     bool run = act && e < last && !ovf;
-    if (run) { cur = __ldg(&a.rec[b]); nxt = __ldg(&a.rec[b + 1]); re = __ldg(&a.rec[e]); sw = (int)cur.y; }
+    const uint32_t Mm1 = a.M - 1;
+    if (run) {
+      cur = __ldg(&a.rec[b]); nxt = __ldg(&a.rec[b + 1]); nxt2 = __ldg(&a.rec[min(b + 2, Mm1)]);
+      re = __ldg(&a.rec[e]); re2 = __ldg(&a.rec[min(e + 1, Mm1)]); sw = (int)cur.y;
+    }
     while (__any_sync(0xffffffffu, run)) {
       if (run) {
         if (P > best) { best = P; first = lastp = (int)cur.y; }
@@ -393,8 +398,8 @@ l2_warp_kernel(const L2WArgs a)
         const int adv = min(d1, d2);
         sw += adv;
         const uint32_t ob = b, oe = e;
-        if (adv == d1) { remove(cur.x, cur.z, ob, oe); b++; cur = nxt; nxt = __ldg(&a.rec[min(b + 1, a.M - 1)]); }
-        if (adv == d2) { insert(re.x, re.z, oe, b); e++; if (e < last) re = __ldg(&a.rec[e]); }
+        if (adv == d1) { remove(cur.x, cur.z, ob, oe); b++; cur = nxt; nxt = nxt2; nxt2 = __ldg(&a.rec[min(b + 2, Mm1)]); }
+        if (adv == d2) { insert(re.x, re.z, oe, b); e++; re = re2; re2 = __ldg(&a.rec[min(e + 1, Mm1)]); }
         run = (e < last) && !ovf;
       }
     }
@@ -679,7 +684,14 @@ void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_
               lw.cPos = cPos.p; lw.cBest = cBest.p; lw.ctr_n2 = d_n2.p;
               const size_t shm = 4 * ((size_t)lw.sLimit + 516 + 32 * (size_t)lw.strideWords);
               static bool attrSet = false;
-              if (!attrSet) { BANI_CUDA(cudaFuncSetAttribute(l2_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attrSet = true; }
+              if (!attrSet) {
+                BANI_CUDA(cudaFuncSetAttribute(l2_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                // leave half of the SM's unified store to L1: the lanes stream their records with 16-byte loads
+                // and re-use each 128-byte line eight times
+                int carve = 50; if (const char *ev = getenv("BANI_L2_CARVEOUT")) carve = atoi(ev);
+                BANI_CUDA(cudaFuncSetAttribute(l2_warp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+                attrSet = true;
+              }
               l2_warp_kernel<<<F, 32, shm, st>>>(lw);
               ctx->launches++;
               // exact slow path for whatever the fast path flagged (uint8 counter overflow, very large sketches)
