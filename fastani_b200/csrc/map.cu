@@ -336,36 +336,38 @@ l2_warp_kernel(const L2WArgs a)
     int t = s, G = 0, P = 0;
     bool ovf = false;
 
-    auto classify = [&](uint32_t h, bool &match) -> int {
-      const uint32_t bkt = h >> 22;
-      int j = tab[bkt]; const int je = tab[bkt + 1];
-      while (j < je && Q[j] < h) j++;
-      match = (j < s) && (Q[j] == h);
-      return j;
-    };
-    auto insert = [&](uint32_t h, uint32_t link, uint32_t idx, uint32_t wb) {
-      const uint32_t pd = link >> 16;
-      if (pd != 0xFFFFu && idx - pd >= wb) return;             // an earlier twin is inside the window
-      bool match; const int j = classify(h, match);
-      if (match) { pres[j >> 5] |= 1u << (j & 31); if (j < t) P++; }
-      else {
-        const uint32_t g = gap[j];
-        if (g == 255u) { ovf = true; return; }
-        gap[j] = (uint8_t)(g + 1);
-        if (j < t) { G++; if (t + G > s) { t--; G -= gap[t]; P -= (pres[t >> 5] >> (t & 31)) & 1; } }
+    // One signed, branch-free update of the window state.  dir = +1: a record enters the window,
+    // dir = -1: it leaves; eff: the record changes the set of DISTINCT window hashes (no twin inside).
+    auto apply = [&](uint32_t h, bool eff, int dir) {
+      const uint32_t bkt = h >> 22;                            // lower_bound of h in Q, inside its bucket
+      int lo = tab[bkt], len = (int)tab[bkt + 1] - lo;
+      while (len > 0) {
+        const int half = len >> 1; const bool lt = Q[lo + half] < h;
+        lo = lt ? lo + half + 1 : lo; len = lt ? len - half - 1 : half;
       }
+      const int j = lo;
+      const bool match = (j < s) && (Q[min(j, s - 1)] == h);
+      const bool m = eff && match, nm = eff && !match;
+      const uint32_t wi = (uint32_t)j >> 5, bit = 1u << (j & 31);
+      const uint32_t w = pres[wi];
+      if (m) pres[wi] = dir > 0 ? (w | bit) : (w & ~bit);
+      const uint32_t g = gap[j];
+      ovf |= nm && dir > 0 && g == 255u;
+      if (nm) gap[j] = (uint8_t)(g + dir);
+      const bool below = j < t;
+      P += (m && below) ? dir : 0;
+      G += (nm && below) ? dir : 0;
+      // the pivot t moves by at most one rank per update
+      const bool down = dir > 0 && (t + G > s);
+      const int tt = t - (down ? 1 : 0);
+      const int gv = gap[tt], pv = (int)((pres[tt >> 5] >> (tt & 31)) & 1u);
+      const bool up = dir < 0 && t < s && (t + 1 + G + gv <= s);
+      G += up ? gv : (down ? -gv : 0);
+      P += up ? pv : (down ? -pv : 0);
+      t += (up ? 1 : 0) - (down ? 1 : 0);
     };
-    auto remove = [&](uint32_t h, uint32_t link, uint32_t idx, uint32_t we) {
-      const uint32_t nd = link & 0xFFFFu;
-      if (nd != 0xFFFFu && idx + nd < we) return;              // a later twin is still inside the window
-      bool match; const int j = classify(h, match);
-      if (match) { pres[j >> 5] &= ~(1u << (j & 31)); if (j < t) P--; }
-      else {
-        gap[j] = (uint8_t)(gap[j] - 1);
-        if (j < t) G--;
-        if (t < s && t + 1 + G + (int)gap[t] <= s) { G += gap[t]; P += (pres[t >> 5] >> (t & 31)) & 1; t++; }
-      }
-    };
+    auto is_new = [](uint32_t link, uint32_t idx, uint32_t wb) { const uint32_t pd = link >> 16; return !(pd != 0xFFFFu && idx - pd >= wb); };
+    auto is_gone = [](uint32_t link, uint32_t idx, uint32_t we) { const uint32_t nd = link & 0xFFFFu; return !(nd != 0xFFFFu && idx + nd < we); };
 
     if (act) {
       const int seq = a.cSeq[c];
@@ -378,7 +380,7 @@ l2_warp_kernel(const L2WArgs a)
     // the first super-window
     uint32_t r = b;
     while (__any_sync(0xffffffffu, act && r < e && !ovf)) {
-      if (act && r < e && !ovf) { const uint4 rc = __ldg(&a.rec[r]); insert(rc.x, rc.z, r, b); r++; }
+      if (act && r < e && !ovf) { const uint4 rc = __ldg(&a.rec[r]); apply(rc.x, is_new(rc.z, r, b), +1); r++; }
     }
     // slide
     int sw = 0, best = 0, first = 0, lastp = 0;
@@ -398,8 +400,13 @@ l2_warp_kernel(const L2WArgs a)
         const int adv = min(d1, d2);
         sw += adv;
         const uint32_t ob = b, oe = e;
-        if (adv == d1) { remove(cur.x, cur.z, ob, oe); b++; cur = nxt; nxt = nxt2; nxt2 = __ldg(&a.rec[min(b + 2, Mm1)]); }
-        if (adv == d2) { insert(re.x, re.z, oe, b); e++; re = re2; re2 = __ldg(&a.rec[min(e + 1, Mm1)]); }
+        const bool doRem = adv == d1, doIns = adv == d2;
+        // the leaving record first (slidingMap.hpp order: delete_ref, then insert_ref); one uniform update
+        // per iteration, a second one only when both ends move together
+        apply(doRem ? cur.x : re.x, doRem ? is_gone(cur.z, ob, oe) : is_new(re.z, oe, ob), doRem ? -1 : +1);
+        if (doRem) { b++; cur = nxt; nxt = nxt2; nxt2 = __ldg(&a.rec[min(b + 2, Mm1)]); }
+        if (doRem && doIns) apply(re.x, is_new(re.z, oe, b), +1);
+        if (doIns) { e++; re = re2; re2 = __ldg(&a.rec[min(e + 1, Mm1)]); }
         run = (e < last) && !ovf;
       }
     }
@@ -680,7 +687,7 @@ void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_
               lw.fragLen = fragLen; lw.cmw = cmw;
               lw.sLimit = std::min(smax, 1024);
               lw.gapWords = (uint32_t)(lw.sLimit + 1 + 3) / 4;
-              lw.strideWords = (lw.gapWords + (uint32_t)(lw.sLimit + 31) / 32) | 1u;      // odd => conflict-free lanes
+              lw.strideWords = (lw.gapWords + (uint32_t)(lw.sLimit + 32) / 32) | 1u;      // odd => conflict-free lanes
               lw.cPos = cPos.p; lw.cBest = cBest.p; lw.ctr_n2 = d_n2.p;
               const size_t shm = 4 * ((size_t)lw.sLimit + 516 + 32 * (size_t)lw.strideWords);
               static bool attrSet = false;
