@@ -91,6 +91,7 @@ void bani_ctx_destroy(bani_ctx *ctx)
   cudaSetDevice(ctx->c.device);
   cudaStreamSynchronize(ctx->c.stream);
   ctx->c.d_minHits.release(); ctx->c.d_rowOff.release(); ctx->c.d_ident.release(); ctx->c.d_upper.release();
+  ctx->c.slots.clear();
   cudaStreamSynchronize(ctx->c.stream);
   cudaStreamDestroy(ctx->c.stream);
   delete ctx;

@@ -5,6 +5,7 @@
 #include <string>
 #include <vector>
 #include <memory>
+#include <map>
 #include <stdexcept>
 #include <cstdio>
 #include <cstdarg>
@@ -120,6 +121,14 @@ struct Index {
   uint64_t totalBins = 0;
 };
 
+// A non-owning typed view of a persistent scratch slot (same surface as DevBuf where it is used).
+template <typename T>
+struct View {
+  T *p = nullptr; size_t n = 0;
+  size_t bytes() const { return n * sizeof(T); }
+  void release() {}
+};
+
 struct Ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -134,7 +143,18 @@ struct Ctx {
   bool profiling = false;
   struct ProfEv { const char *name; cudaEvent_t a, b; double bytes; };
   std::vector<ProfEv> profEvents;
+  // Grow-only scratch slots for the per-chunk working set of the mapping pipeline (hit keys, flags,
+  // candidate arrays ...): after the first chunk nothing is allocated or freed inside the timed path.
+  std::map<int, DevBuf<uint8_t>> slots;
+  template <typename T> View<T> view(int id, size_t n)
+  {
+    DevBuf<uint8_t> &b = slots[id];
+    const size_t bytes = (n ? n : 1) * sizeof(T);
+    if (b.n < bytes) b.alloc(bytes + bytes / 8 + 256, stream);
+    View<T> v; v.p = (T *)b.p; v.n = n; return v;
+  }
 };
+#define BANI_SCRATCH(T, name, count) ::bani::View<T> name = ctx->view<T>(__LINE__, (count))
 
 // RAII stage timer: records an event pair around a stage when profiling is on.
 struct Stage {

@@ -581,22 +581,24 @@ void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_
     if (wantCgi) { hCount.assign((size_t)nQc * nG, 0); hIdent.assign((size_t)nQc * nG, 0.f); }
 
     if (F > 0 && ix->M > 0) {
-      DevBuf<SeqDesc> d_desc(F, st);
+      BANI_SCRATCH(SeqDesc, d_desc, F);
       BANI_CUDA(cudaMemcpyAsync(d_desc.p, desc.data(), sizeof(SeqDesc) * (size_t)F, cudaMemcpyHostToDevice, st));
-      DevBuf<int32_t> d_fragQuery(F, st), d_fragSeqId(F, st);
+      BANI_SCRATCH(int32_t, d_fragQuery, F);
+      BANI_SCRATCH(int32_t, d_fragSeqId, F);
       BANI_CUDA(cudaMemcpyAsync(d_fragQuery.p, fragQuery.data(), 4 * (size_t)F, cudaMemcpyHostToDevice, st));
       { std::vector<int32_t> ids(F); for (int i = 0; i < F; i++) ids[i] = desc[i].seqId;
         BANI_CUDA(cudaMemcpyAsync(d_fragSeqId.p, ids.data(), 4 * (size_t)F, cudaMemcpyHostToDevice, st));
         BANI_CUDA(cudaStreamSynchronize(st)); }
 
       // ---- A: fragment sketches
-      DevBuf<uint32_t> fragHash, segStart((size_t)F + 1, st);
+      View<uint32_t> fragHash;
+      BANI_SCRATCH(uint32_t, segStart, (size_t)F + 1);
       uint64_t perFrag = std::max(1, fragLen - k + 1);
       uint64_t cap = std::min<uint64_t>((uint64_t)F * perFrag, (uint64_t)F * (uint64_t)(2.6 * fragLen / (w + 1) + 64));
       uint64_t T = 0;
       for (int attempt = 0; attempt < 2; attempt++) {
         if (cap > 0xfffffff0ull) fail(BANI_ERR_LIMIT, "query chunk produces more than 2^32 minimizers");
-        fragHash.alloc(std::max<uint64_t>(cap, 1), st);
+        fragHash = ctx->view<uint32_t>(__LINE__, std::max<uint64_t>(cap, 1));
         Stage sg(ctx, "q_sketch", (double)F * fragLen / 4.0);
         T = sketch_sequences(ctx, d_desc.p, F, flen.data(), fragHash.p, nullptr, nullptr, cap, segStart.p);
         if (T <= cap) break;
@@ -604,7 +606,8 @@ void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_
       }
 
       // ---- B: sorted unique hashes per fragment
-      DevBuf<int32_t> sCount(F, st); DevBuf<int> d_flags(2, st);
+      BANI_SCRATCH(int32_t, sCount, F);
+      DevBuf<int> d_flags(2, st);
       BANI_CUDA(cudaMemsetAsync(d_flags.p, 0, 8, st));
       { Stage sg(ctx, "q_sort_unique", 8.0 * T);
         sort_unique_kernel<<<F, SU_THREADS, 0, st>>>(fragHash.p, segStart.p, F, sCount.p, d_flags.p, d_flags.p + 1); ctx->launches++; }
@@ -617,13 +620,15 @@ void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_
 
       if (T > 0 && smax > 0) {
         // ---- C: lookup
-        DevBuf<uint32_t> hitLo(T + 1, st), hitCnt(T + 1, st);
-        DevBuf<unsigned long long> hitOff(T + 1, st);
+        BANI_SCRATCH(uint32_t, hitLo, T + 1);
+        BANI_SCRATCH(uint32_t, hitCnt, T + 1);
+        BANI_SCRATCH(unsigned long long, hitOff, T + 1);
         { Stage sg(ctx, "lookup", 12.0 * T);
           lookup_kernel<<<nblk(T + 1), 256, 0, st>>>(fragHash.p, segStart.p, sCount.p, F, (uint32_t)T, ix->ukeys.p, ix->uoff.p,
                                                    ix->dir.p, ix->dirBits, hitLo.p, hitCnt.p);
           ctx->launches++;
-          size_t tb = cub_scan_u64_temp(T + 1); DevBuf<uint8_t> tmp(tb, st);
+          size_t tb = cub_scan_u64_temp(T + 1);
+          BANI_SCRATCH(uint8_t, tmp, tb);
           cub_exclusive_sum_u32_to_u64(tmp.p, tb, hitCnt.p, (uint64_t *)hitOff.p, T + 1, st); }
         unsigned long long N = 0;
         BANI_CUDA(cudaMemcpyAsync(&N, hitOff.p + T, 8, cudaMemcpyDeviceToHost, st));
@@ -635,23 +640,27 @@ void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_
 
         if (N > 0) {
           // ---- D: gather + sort
-          DevBuf<unsigned long long> keysA(N, st), keysB(N, st);
+          BANI_SCRATCH(unsigned long long, keysA, N);
+          BANI_SCRATCH(unsigned long long, keysB, N);
           { Stage sg(ctx, "hit_gather", 12.0 * N);
             gather_kernel<<<nblk(T), 256, 0, st>>>(segStart.p, F, (uint32_t)T, hitLo.p, hitCnt.p, hitOff.p, ix->posIdx.p, keysA.p); ctx->launches++; }
           int fbits = 1; while ((1ll << fbits) < F) fbits++;
           { Stage sg(ctx, "hit_sort", 16.0 * N);
-            size_t tb = cub_sort_keys_u64_temp(N); DevBuf<uint8_t> tmp(tb, st);
+            size_t tb = cub_sort_keys_u64_temp(N);
+            BANI_SCRATCH(uint8_t, tmp, tb);
             cub_sort_keys_u64(tmp.p, tb, (const uint64_t *)keysA.p, (uint64_t *)keysB.p, N, 0, 32 + fbits, st); }
           keysA.release();
 
           // ---- E: L1 candidate regions
           L1Args la; la.keys = keysB.p; la.N = N; la.segStart = segStart.p; la.hitOff = hitOff.p; la.sCount = sCount.p;
           la.minHits = ctx->d_minHits.p; la.recSeq = ix->seqId.p; la.recWpos = ix->wpos.p; la.fragLen = fragLen;
-          DevBuf<uint32_t> head(N + 1, st), headScan(N + 1, st);
+          BANI_SCRATCH(uint32_t, head, N + 1);
+          BANI_SCRATCH(uint32_t, headScan, N + 1);
           { Stage sg(ctx, "l1_flags", 8.0 * N);
             l1_flag_kernel<<<nblk(N + 1), 256, 0, st>>>(la, head.p);
             ctx->launches++;
-            size_t tb = cub_scan_u32_temp(N + 1); DevBuf<uint8_t> tmp(tb, st);
+            size_t tb = cub_scan_u32_temp(N + 1);
+            BANI_SCRATCH(uint8_t, tmp, tb);
             cub_exclusive_sum_u32(tmp.p, tb, head.p, headScan.p, N + 1, st); }
           uint32_t C = 0;
           BANI_CUDA(cudaMemcpyAsync(&C, headScan.p + N, 4, cudaMemcpyDeviceToHost, st));
@@ -659,7 +668,12 @@ void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_
           out.ctr.candidates += C;
 
           if (C > 0) {
-            DevBuf<int32_t> cFrag(C, st), cSeq(C, st), cStart(C, st), cEnd(C, st), cPos(C, st), cBest(C, st);
+            BANI_SCRATCH(int32_t, cFrag, C);
+            BANI_SCRATCH(int32_t, cSeq, C);
+            BANI_SCRATCH(int32_t, cStart, C);
+            BANI_SCRATCH(int32_t, cEnd, C);
+            BANI_SCRATCH(int32_t, cPos, C);
+            BANI_SCRATCH(int32_t, cBest, C);
             { Stage sg(ctx, "l1_write", 8.0 * N);
               l1_write_kernel<<<nblk(N), 256, 0, st>>>(la, head.p, headScan.p, cFrag.p, cSeq.p, cStart.p, cEnd.p); ctx->launches++; }
             head.release(); headScan.release(); keysB.release();
@@ -671,14 +685,14 @@ void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_
             l2.fragLen = fragLen; l2.cmw = cmw; l2.smax = smax;
             l2.stride = ((size_t)2 * (smax + 2) + smax + 15) / 16 * 16;
             const unsigned blocks = (unsigned)std::min<uint64_t>((C + 63) / 64, (uint64_t)ctx->smCount * 16);
-            DevBuf<uint8_t> scratch((size_t)blocks * 64 * l2.stride, st);
-            DevBuf<unsigned long long> d_n2(1, st);
+            BANI_SCRATCH(uint8_t, scratch, (size_t)blocks * 64 * l2.stride);
+            BANI_SCRATCH(unsigned long long, d_n2, 1);
             BANI_CUDA(cudaMemsetAsync(d_n2.p, 0, 8, st));
             l2.scratch = scratch.p; l2.cPos = cPos.p; l2.cBest = cBest.p; l2.ctr_n2 = d_n2.p; l2.onlyFlagged = 1;
             {
               Stage sg(ctx, "l2");
               // fast path: one warp per fragment, window state in shared memory
-              DevBuf<uint32_t> fragCandOff((size_t)F + 1, st);
+              BANI_SCRATCH(uint32_t, fragCandOff, (size_t)F + 1);
               frag_cand_off_kernel<<<nblk((uint64_t)F + 1), 256, 0, st>>>(cFrag.p, C, F, fragCandOff.p);
               ctx->launches++;
               L2WArgs lw; lw.cSeq = cSeq.p; lw.cStart = cStart.p; lw.cEnd = cEnd.p; lw.fragCandOff = fragCandOff.p;
@@ -693,9 +707,9 @@ void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_
               static bool attrSet = false;
               if (!attrSet) {
                 BANI_CUDA(cudaFuncSetAttribute(l2_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                // leave half of the SM's unified store to L1: the lanes stream their records with 16-byte loads
+                // shared-memory carve-out: occupancy (window state per lane) beats L1 capacity here (measured 25/50/75/100 %)
                 // and re-use each 128-byte line eight times
-                int carve = 50; if (const char *ev = getenv("BANI_L2_CARVEOUT")) carve = atoi(ev);
+                int carve = 100; if (const char *ev = getenv("BANI_L2_CARVEOUT")) carve = atoi(ev);
                 BANI_CUDA(cudaFuncSetAttribute(l2_warp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
                 attrSet = true;
               }
@@ -709,10 +723,12 @@ void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_
             RepArgs ra; ra.cFrag = cFrag.p; ra.cSeq = cSeq.p; ra.cPos = cPos.p; ra.cBest = cBest.p; ra.C = C;
             ra.sCount = sCount.p; ra.fragSeqId = d_fragSeqId.p; ra.rowOff = ctx->d_rowOff.p; ra.ident = ctx->d_ident.p;
             ra.upper = ctx->d_upper.p; ra.pid = pid; ra.fragLen = fragLen;
-            DevBuf<uint32_t> keep(C + 1, st), keepScan(C + 1, st);
+            BANI_SCRATCH(uint32_t, keep, C + 1);
+            BANI_SCRATCH(uint32_t, keepScan, C + 1);
             keep_flag_kernel<<<nblk(C + 1), 256, 0, st>>>(ra, keep.p);
             ctx->launches++;
-            { size_t tb = cub_scan_u32_temp(C + 1); DevBuf<uint8_t> tmp(tb, st);
+            { size_t tb = cub_scan_u32_temp(C + 1);
+            BANI_SCRATCH(uint8_t, tmp, tb);
               cub_exclusive_sum_u32(tmp.p, tb, keep.p, keepScan.p, C + 1, st); }
             uint32_t R = 0; unsigned long long n2 = 0;
             BANI_CUDA(cudaMemcpyAsync(&R, keepScan.p + C, 4, cudaMemcpyDeviceToHost, st));
@@ -720,7 +736,8 @@ void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_
             BANI_CUDA(cudaStreamSynchronize(st));
             out.ctr.n2 += n2; out.ctr.mappings += R;
             if (R > 0) {
-              DevBuf<bani_mapping> rows(R, st); DevBuf<int32_t> rFrag(R, st);
+              BANI_SCRATCH(bani_mapping, rows, R);
+              DevBuf<int32_t> rFrag(R, st);
               { Stage sg(ctx, "report", 44.0 * R);
                 rows_kernel<<<nblk(C), 256, 0, st>>>(ra, keep.p, keepScan.p, rows.p, rFrag.p); ctx->launches++; }
               if (wantRows) {
@@ -739,7 +756,8 @@ void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_
                 CgiArgs ca; ca.rows = rows.p; ca.rFrag = rFrag.p; ca.R = R; ca.fragQuery = d_fragQuery.p;
                 ca.contigGenome = ix->contigGenome.p; ca.contigBinOff = ix->contigBinOff.p; ca.fragLen = fragLen;
                 ca.totalBins = ix->totalBins; ca.nGenomes = nG; ca.table = table.p; ca.touched = touched.p;
-                DevBuf<int32_t> oCount((size_t)nQc * nG, st); DevBuf<float> oIdent((size_t)nQc * nG, st);
+                BANI_SCRATCH(int32_t, oCount, (size_t)nQc * nG);
+                DevBuf<float> oIdent((size_t)nQc * nG, st);
                 { Stage sg(ctx, "cgi", 48.0 * R);
                   cgi_scatter_kernel<<<nblk(R), 256, 0, st>>>(ca);
                   ctx->launches++;
