@@ -75,11 +75,8 @@ int bani_ctx_create(int device, const bani_params *p, bani_ctx **out)
   cudaDeviceProp prop;
   BANI_CUDA(cudaGetDeviceProperties(&prop, device));
   c->c.smCount = prop.multiProcessorCount;
+  dev_cache_flush(device);                   // blocks cached under streams of destroyed contexts
   BANI_CUDA(cudaStreamCreateWithFlags(&c->c.stream, cudaStreamNonBlocking));
-  cudaMemPool_t pool;
-  BANI_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-  uint64_t thr = UINT64_MAX;
-  BANI_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
   *out = c.release();
   return BANI_OK;
   BANI_CATCH
@@ -93,6 +90,7 @@ void bani_ctx_destroy(bani_ctx *ctx)
   ctx->c.d_minHits.release(); ctx->c.d_rowOff.release(); ctx->c.d_ident.release(); ctx->c.d_upper.release();
   ctx->c.slots.clear();
   cudaStreamSynchronize(ctx->c.stream);
+  dev_cache_flush(ctx->c.device);            // blocks are keyed by stream: return them before it dies
   cudaStreamDestroy(ctx->c.stream);
   delete ctx;
 }

@@ -32,26 +32,29 @@ void set_last_error(const std::string &m);
   ::bani::fail(BANI_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 
 // ---------------------------------------------------------------- device memory
-// Stream-ordered allocation from the device's default memory pool (release
-// threshold raised in Ctx so freed blocks are recycled, not returned to the OS).
+// DevBuf owns a block from the caching allocator of alloc.cpp (freed blocks are reused on the same
+// stream; the driver is only called on a miss).
+void *dev_alloc(size_t bytes, cudaStream_t st, size_t *granted);
+void  dev_free(void *p, size_t granted, cudaStream_t st);
+void  dev_cache_flush(int dev);
+
 template <typename T>
 struct DevBuf {
-  T *p = nullptr; size_t n = 0; cudaStream_t st = nullptr;
+  T *p = nullptr; size_t n = 0; cudaStream_t st = nullptr; size_t granted = 0;
   DevBuf() {}
   DevBuf(size_t n_, cudaStream_t s) { alloc(n_, s); }
   DevBuf(const DevBuf &) = delete; DevBuf &operator=(const DevBuf &) = delete;
-  DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), st(o.st) { o.p = nullptr; o.n = 0; }
-  DevBuf &operator=(DevBuf &&o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; st = o.st; o.p = nullptr; o.n = 0; } return *this; }
+  DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), st(o.st), granted(o.granted) { o.p = nullptr; o.n = 0; }
+  DevBuf &operator=(DevBuf &&o) noexcept
+  { if (this != &o) { release(); p = o.p; n = o.n; st = o.st; granted = o.granted; o.p = nullptr; o.n = 0; } return *this; }
   ~DevBuf() { release(); }
   void alloc(size_t n_, cudaStream_t s)
   {
     release(); n = n_; st = s;
     if (n == 0) return;
-    cudaError_t e = cudaMallocAsync((void **)&p, n * sizeof(T), s);
-    if (e != cudaSuccess) { p = nullptr; size_t want = n * sizeof(T); n = 0; (void)cudaGetLastError();
-      fail(BANI_ERR_NOMEM, "device allocation of %zu bytes failed: %s", want, cudaGetErrorString(e)); }
+    p = (T *)dev_alloc(n * sizeof(T), s, &granted);
   }
-  void release() { if (p) { cudaFreeAsync(p, st); p = nullptr; } n = 0; }
+  void release() { if (p) { dev_free(p, granted, st); p = nullptr; } n = 0; }
   size_t bytes() const { return n * sizeof(T); }
 };
 

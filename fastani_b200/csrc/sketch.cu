@@ -34,6 +34,10 @@ static constexpr int SK_SLOTS = SK_THREADS * SK_P;    // 4096 hash slots per CTA
 static constexpr int SK_WMAX = 1024;
 static constexpr int SK_KMAX = 32;
 static constexpr int SK_ASCII = SK_SLOTS + SK_KMAX + 64;   // bytes staged per CTA (16-aligned start + slack)
+// Key slots are padded by one per 16 so that the 16-position runs of consecutive lanes start in different
+// banks (a lane stride of 17 keys = 34 words): without it every 64-bit key access is a 32-way conflict.
+#define KIDX(q) ((q) + ((q) >> 4))
+static constexpr int SK_KEYS = SK_SLOTS + SK_SLOTS / 16;
 
 struct SketchArgs {
   const SeqDesc *desc; const uint32_t *tileOff;   // nSeq+1
@@ -161,7 +165,7 @@ __global__ void __launch_bounds__(SK_THREADS)
 sketch_kernel(const SketchArgs a)
 {
   __shared__ __align__(16) uint8_t  s_ascii[SK_ASCII];
-  __shared__ __align__(16) uint64_t s_key[SK_SLOTS];
+  __shared__ __align__(16) uint64_t s_key[SK_KEYS];
   __shared__ uint16_t s_vmask[SK_THREADS];
   __shared__ uint32_t s_wsum[SK_THREADS / 32];
   __shared__ unsigned long long s_base;
@@ -220,12 +224,12 @@ sketch_kernel(const SketchArgs a)
           vmask |= 1u << j;
         }
       }
-      s_key[q0 + j] = key;
+      s_key[KIDX(q0 + j)] = key;
       window_slide<KT>(sp[j + k], k, F, R);
     }
   } else {
 #pragma unroll
-    for (int j = 0; j < SK_P; j++) s_key[q0 + j] = ~0ull;
+    for (int j = 0; j < SK_P; j++) s_key[KIDX(q0 + j)] = ~0ull;
   }
   s_vmask[tid] = (uint16_t)vmask;
   __syncthreads();
@@ -237,21 +241,21 @@ sketch_kernel(const SketchArgs a)
     const int g0 = q0 + g;
     // A = min keys[g0+G-w .. g0]   (common to all G windows of the group)
     uint64_t A = ~0ull;
-    for (int q = max(0, g0 + G - w); q <= g0; q++) A = min64(A, s_key[q]);
+    for (int q = max(0, g0 + G - w); q <= g0; q++) A = min64(A, s_key[KIDX(q)]);
     uint64_t S[G];
     S[G - 1] = A;
 #pragma unroll
-    for (int r = G - 1; r >= 1; r--) { int q = g0 + r - w; S[r - 1] = (q >= 0) ? min64(S[r], s_key[q]) : S[r]; }
+    for (int r = G - 1; r >= 1; r--) { int q = g0 + r - w; S[r - 1] = (q >= 0) ? min64(S[r], s_key[KIDX(q)]) : S[r]; }
     uint64_t Pr = ~0ull;
 #pragma unroll
     for (int r = 0; r < G; r++) {
-      if (r > 0) Pr = min64(Pr, s_key[g0 + r]);
+      if (r > 0) Pr = min64(Pr, s_key[KIDX(g0 + r)]);
       M[g + r] = min64(S[r], Pr);
     }
   }
   __syncthreads();
 #pragma unroll
-  for (int j = 0; j < SK_P; j++) s_key[q0 + j] = M[j];
+  for (int j = 0; j < SK_P; j++) s_key[KIDX(q0 + j)] = M[j];
   __syncthreads();
 
   // ---- phase 4: emission flags
@@ -274,7 +278,7 @@ sketch_kernel(const SketchArgs a)
         }
         if (qp < qlo) qp = -1;
       }
-      if (qp < 0 || s_key[qp] != s_key[q]) emit |= 1u << j;
+      if (qp < 0 || s_key[KIDX(qp)] != s_key[KIDX(q)]) emit |= 1u << j;
     }
   }
   const uint32_t cnt = __popc(emit);
@@ -323,7 +327,7 @@ sketch_kernel(const SketchArgs a)
   for (uint32_t em = emit; em; em &= em - 1, o++) {
     const int j = __ffs(em) - 1;
     if (o < a.cap) {
-      a.o_hash[o] = (uint32_t)(s_key[q0 + j] >> 32);
+      a.o_hash[o] = (uint32_t)(s_key[KIDX(q0 + j)] >> 32);
       if (a.o_wpos)  a.o_wpos[o] = hs + q0 + j - w + 1;
       if (a.o_seqId) a.o_seqId[o] = d.seqId;
     }
