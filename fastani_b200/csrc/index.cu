@@ -63,11 +63,41 @@ __global__ void dir_kernel(const uint32_t *ukeys, uint32_t U, int dirBits, uint3
   if (i == U - 1) for (uint32_t b = bc + 1; b <= (1u << dirBits); b++) dir[b] = U;
 }
 
+// One 16-byte record per minimizer for the L2 stream: x = hash, y = wpos | tie << 31, z = twin link,
+// w = back | fwd << 16.  back / fwd / tie describe the L2 super-window geometry of computeL2MappedRegions
+// (computeMap.hpp:418-497) around this record, which does not depend on the candidate (cmw is fixed):
+//   back : records strictly after the window start when this record ENTERS the window, i.e.
+//          x - (UB(w_x - cmw + 1) - 1), UB = first record of the contig with wpos > v
+//   fwd  : LB(w_{x+1} + cmw - 1) - x, the window end (exclusive) when this record LEAVES the window
+//          (0xFFFF for the last record of a contig: it never leaves inside a scored window)
+//   tie  : the record at x + fwd enters in the same step in which x leaves (wpos equal to w_{x+1} + cmw - 1)
+// so the event schedule of a candidate needs no search (map.cu, l2_events_kernel).
 __global__ void zip_records_kernel(const uint32_t *hash, const int32_t *wpos, const uint32_t *link, const int32_t *seqId,
-                                   uint64_t n, uint4 *rec)
+                                   const uint32_t *contigRecOff, int cmw, uint64_t n, uint4 *rec)
 {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) rec[i] = make_uint4(hash[i], (uint32_t)wpos[i], link[i], (uint32_t)seqId[i]);
+  uint64_t i64 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i64 >= n) return;
+  const uint32_t i = (uint32_t)i64;
+  const int32_t wx = wpos[i];
+  const int seq = seqId[i];
+  const uint32_t lo = contigRecOff[seq], hi = contigRecOff[seq + 1];
+  uint32_t back = 0, fwd = 0xFFFFu, tie = 0;
+  if (cmw >= 2) {
+    { // UB(wx - cmw + 1) over [lo, i]: the answer is within cmw records of i
+      const int32_t v = wx - cmw + 1;
+      uint32_t l = (i - lo > (uint32_t)cmw) ? i - (uint32_t)cmw : lo, h = i;
+      while (l < h) { uint32_t m = (l + h) >> 1; if (wpos[m] <= v) l = m + 1; else h = m; }
+      back = min(i - l + 1, 0xFFFFu);
+    }
+    if (i + 1 < hi) {
+      const int32_t v = wpos[i + 1] + cmw - 1;
+      uint32_t l = i + 1, h = (hi - i - 1 > (uint32_t)cmw + 1) ? i + 1 + (uint32_t)cmw + 1 : hi;
+      while (l < h) { uint32_t m = (l + h) >> 1; if (wpos[m] < v) l = m + 1; else h = m; }
+      fwd = min(l - i, 0xFFFEu);
+      tie = (l < hi && wpos[l] == v) ? 1u : 0u;
+    }
+  }
+  rec[i] = make_uint4(hash[i], (uint32_t)wx | (tie << 31), link[i], back | (fwd << 16));
 }
 
 __global__ void dir_fill_kernel(const uint32_t *ukeys, uint32_t U, int dirBits, uint32_t *dir)
@@ -224,7 +254,8 @@ Index *index_build(Ctx *ctx, Genome *const *refs, int32_t nRefs)
   dir_fill_kernel<<<nblk((1ull << bits) + 1), 256, 0, st>>>(ix->ukeys.p, (uint32_t)U, bits, ix->dir.p);
   ctx->launches++;
   ix->rec.alloc(M, st);
-  zip_records_kernel<<<nblk(M), 256, 0, st>>>(ix->hash.p, ix->wpos.p, ix->link.p, ix->seqId.p, M, ix->rec.p);
+  ix->cmw = fragLen - (w - 1) - (k - 1);                   // computeMap.hpp:427
+  zip_records_kernel<<<nblk(M), 256, 0, st>>>(ix->hash.p, ix->wpos.p, ix->link.p, ix->seqId.p, ix->contigRecOff.p, ix->cmw, M, ix->rec.p);
   ctx->launches++;
   sgc.stop();
   BANI_CUDA(cudaGetLastError());

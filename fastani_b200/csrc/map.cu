@@ -196,7 +196,6 @@ struct L2Args {
   int fragLen, cmw, smax;
   uint8_t *scratch; size_t stride;
   int32_t *cPos, *cBest;
-  unsigned long long *ctr_n2;
   int onlyFlagged;
 };
 
@@ -218,7 +217,6 @@ l2_kernel(const L2Args a)
   const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x, nslots = gridDim.x * blockDim.x;
   uint16_t *gap = (uint16_t *)(a.scratch + (size_t)slot * a.stride);
   uint8_t *pres = (uint8_t *)(gap + a.smax + 2);
-  unsigned long long n2 = 0;
   for (uint32_t c = slot; c < a.C; c += nslots) {
     if (a.onlyFlagged && a.cBest[c] != -1) continue;           // the fast path already solved it
     const int f = a.cFrag[c];
@@ -229,7 +227,6 @@ l2_kernel(const L2Args a)
     uint32_t b = lb_wpos(a.recWpos, lo, hi, a.cStart[c]);
     uint32_t e = lb_wpos(a.recWpos, lo, hi, a.recWpos[b] + a.cmw);
     const uint32_t last = lb_wpos(a.recWpos, lo, hi, a.cEnd[c] + a.fragLen);
-    n2 += last - b;
     for (int i = 0; i <= s; i++) gap[i] = 0;
     for (int i = 0; i < s; i++) pres[i] = 0;
     int t = s, G = 0, P = 0;
@@ -267,21 +264,38 @@ l2_kernel(const L2Args a)
     a.cPos[c] = (first + lastp) / 2;
     a.cBest[c] = best;
   }
-  if (n2) atomicAdd(a.ctr_n2, n2);
 }
 
-// ------------------------------------------------------------------ F': L2 fast path, one warp per query fragment
-// All candidate regions of one fragment share its sketch Q, so a warp stages Q (plus a 1024-bucket
-// directory over the top 10 hash bits) in shared memory once and gives every lane one candidate.
-// Per-lane window state lives in shared memory too: gap[g] = distinct non-Q window hashes with exactly
-// g query hashes below them (uint8, overflow => the candidate is handed to the exact slow kernel),
-// pres = bitmap of query hashes present in the window.  Records are read as 16-byte AoS
-// (hash, wpos, twin link, seqId): one load per pointer advance.
-struct L2WArgs {
-  const int32_t *cSeq, *cStart, *cEnd; const uint32_t *fragCandOff;
+// ------------------------------------------------------------------ F': L2 fast path = parallel pre-pass + lean sequential pass
+// computeL2MappedRegions is a sequential sweep per candidate, but everything in it that does not depend on
+// the sweep state can be computed for all (candidate, record) pairs in parallel:
+//   l2_bounds_kernel  lane per candidate: b0 / e0 / last (the three lower_bounds of computeMap.hpp:424-436) and
+//                     the exact number of window events
+//   l2_events_kernel  CTA per fragment (its sketch Q + a bucket directory in shared memory), lane per record:
+//                     rank of the record's hash in Q, match bit, and -- from the per-record window links
+//                     back / fwd / tie stored in the index (index.cu) -- the exact position of its "enters"
+//                     and "leaves" events in the candidate's event stream, whether the event changes the set of
+//                     DISTINCT window hashes (twin links), and whether a scoring point follows it.
+//                     One 16-bit code per event: j[0:10] | match<<11 | insert<<12 | effective<<13 | score<<14.
+//   l2_seq_kernel     lane per candidate (candidates ordered by event count so a warp's lanes finish together):
+//                     streams the 16-bit codes (16-byte loads, one ahead) through the rank-space window state
+//                     (gap[] uint8 + pres bitmap per lane in shared memory, word-interleaved across lanes so that
+//                     every access is bank-conflict free whatever the ranks are).
+// Counter overflow (255 distinct foreign hashes between two neighbouring query hashes) or s > 2047 hands the
+// candidate to the exact global-memory kernel above.
+static constexpr int L2_JBITS = 11, L2_JMASK = (1 << L2_JBITS) - 1;
+static constexpr uint32_t EV_M = 1u << 11, EV_D = 1u << 12, EV_E = 1u << 13, EV_S = 1u << 14;
+
+struct L2PArgs {
+  const int32_t *cFrag, *cSeq, *cStart, *cEnd; uint32_t C;
+  const uint32_t *fragCandOff;
   const uint32_t *fragHash; const uint32_t *segStart; const int32_t *sCount;
-  const uint4 *rec; const uint32_t *contigRecOff; uint32_t M;
-  int fragLen, cmw, sLimit; uint32_t strideWords, gapWords;
+  const uint4 *rec; const uint32_t *contigRecOff;
+  int fragLen, cmw, sLimit, dirShift;
+  uint32_t *cB0, *cE0, *cLast, *cNEv, *cChunks;   // per candidate
+  const uint32_t *cOff;                            // stream offset in 16-byte units
+  uint16_t *events;
+  const uint32_t *perm; uint32_t gapWords, laneWords;
   int32_t *cPos, *cBest; unsigned long long *ctr_n2;
 };
 
@@ -294,130 +308,191 @@ __global__ void frag_cand_off_kernel(const int32_t *cFrag, uint32_t C, int32_t F
   fragCandOff[f] = lo;
 }
 
+__device__ __forceinline__ int32_t rec_wpos(const uint4 *rec, uint32_t i) { return (int32_t)(__ldg(&rec[i].y) & 0x7FFFFFFFu); }
 __device__ __forceinline__ uint32_t lb_rec(const uint4 *rec, uint32_t lo, uint32_t hi, int32_t v)
 {
-  while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if ((int32_t)__ldg(&rec[mid]).y < v) lo = mid + 1; else hi = mid; }
+  while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (rec_wpos(rec, mid) < v) lo = mid + 1; else hi = mid; }
   return lo;
 }
 
-__global__ void __launch_bounds__(32)
-l2_warp_kernel(const L2WArgs a)
+__global__ void l2_bounds_kernel(const L2PArgs a)
+{
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long n2 = 0;
+  if (c < a.C) {
+    const int seq = a.cSeq[c];
+    const uint32_t lo = a.contigRecOff[seq], hi = a.contigRecOff[seq + 1];
+    const uint32_t b0 = lb_rec(a.rec, lo, hi, a.cStart[c]);
+    const uint32_t e0 = lb_rec(a.rec, b0, hi, rec_wpos(a.rec, b0) + a.cmw);
+    const uint32_t last = lb_rec(a.rec, b0, hi, a.cEnd[c] + a.fragLen);
+    n2 = last - b0;
+    const int s = a.sCount[a.cFrag[c]];
+    uint32_t nEv = 0;
+    if (e0 < last) {
+      // removals scheduled = window start after the step in which record last-1 enters
+      const uint32_t back = __ldg(&a.rec[last - 1].w) & 0xFFFFu;
+      const uint32_t bEnd = (back > last - 1 - b0) ? b0 : last - 1 - back;
+      nEv = (e0 - b0) + (last - e0) + (bEnd - b0);
+    }
+    a.cB0[c] = b0; a.cE0[c] = e0; a.cLast[c] = last;
+    const bool fast = s >= 1 && s <= a.sLimit;
+    a.cNEv[c] = fast ? nEv : 0u;
+    a.cChunks[c] = fast ? (nEv + 7) >> 3 : 0u;
+    a.cBest[c] = fast ? 0 : -1;                 // -1: exact slow kernel
+    a.cPos[c] = 0;
+  } else if (c == a.C) a.cChunks[c] = 0;
+  for (int o = 16; o; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+  if ((threadIdx.x & 31) == 0 && n2) atomicAdd(a.ctr_n2, n2);
+}
+
+__global__ void l2_sortkey_kernel(const uint32_t *cNEv, uint32_t C, uint32_t *key, uint32_t *val)
+{
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  key[c] = 0xFFFFFu - min(cNEv[c], 0xFFFFFu);   // ascending sort => longest streams first
+  val[c] = c;
+}
+
+static constexpr int L2E_THREADS = 256;
+
+__global__ void __launch_bounds__(L2E_THREADS)
+l2_events_kernel(const L2PArgs a)
 {
   extern __shared__ __align__(16) uint32_t smem[];
-  const int f = blockIdx.x, lane = threadIdx.x;
+  const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const uint32_t c0 = a.fragCandOff[f], c1 = a.fragCandOff[f + 1];
   if (c0 == c1) return;
   const int s = a.sCount[f];
-  if (s > a.sLimit || s < 1) { for (uint32_t c = c0 + lane; c < c1; c += 32) a.cBest[c] = -1; return; }
+  if (s < 1 || s > a.sLimit) return;
   uint32_t *Q = smem;                                          // sLimit words
-  uint16_t *tab = (uint16_t *)(smem + a.sLimit);               // 1025 entries (+ pad)
-  uint32_t *stBase = smem + a.sLimit + 516;
-  uint32_t *st = stBase + lane * a.strideWords;                // this lane's state
-  uint8_t *gap = (uint8_t *)st;                                // s + 1 counters
-  uint32_t *pres = st + a.gapWords;                            // bitmap of s bits
+  uint16_t *tab = (uint16_t *)(smem + a.sLimit);               // 1025 entries
   {
     const uint32_t *Qg = a.fragHash + a.segStart[f];
-    for (int i = lane; i < s; i += 32) Q[i] = Qg[i];
-    __syncwarp();
-    for (int bkt = lane; bkt <= 1024; bkt += 32) {
+    for (int i = tid; i < s; i += L2E_THREADS) Q[i] = Qg[i];
+    __syncthreads();
+    for (int bkt = tid; bkt <= 1024; bkt += L2E_THREADS) {
       int lo = 0, hi = s;
       if (bkt == 1024) lo = s;
-      else { const uint32_t v = (uint32_t)bkt << 22; while (lo < hi) { int mid = (lo + hi) >> 1; if (Q[mid] < v) lo = mid + 1; else hi = mid; } }
+      else { const uint32_t v = (uint32_t)bkt << a.dirShift; while (lo < hi) { int mid = (lo + hi) >> 1; if (Q[mid] < v) lo = mid + 1; else hi = mid; } }
       tab[bkt] = (uint16_t)lo;
     }
-    __syncwarp();
+    __syncthreads();
   }
-  unsigned long long n2 = 0;
-  for (uint32_t cb = c0; cb < c1; cb += 32) {
-    const uint32_t c = cb + lane;
-    const bool act = c < c1;
-    for (uint32_t i = 0; i < a.strideWords; i++) st[i] = 0;
-    uint32_t b = 0, e = 0, last = 0;
-    int t = s, G = 0, P = 0;
-    bool ovf = false;
-
-    // One signed, branch-free update of the window state.  dir = +1: a record enters the window,
-    // dir = -1: it leaves; eff: the record changes the set of DISTINCT window hashes (no twin inside).
-    auto apply = [&](uint32_t h, bool eff, int dir) {
-      const uint32_t bkt = h >> 22;                            // lower_bound of h in Q, inside its bucket
+  for (uint32_t c = c0 + wid; c < c1; c += L2E_THREADS / 32) {
+    const uint32_t nEv = a.cNEv[c];
+    if (nEv == 0) continue;
+    const uint32_t b0 = a.cB0[c], e0 = a.cE0[c], last = a.cLast[c], nInit = e0 - b0;
+    uint16_t *ev = a.events + (size_t)a.cOff[c] * 8;
+    for (uint32_t r = b0 + lane; r < last; r += 32) {
+      const uint4 rc = __ldg(&a.rec[r]);
+      const uint32_t h = rc.x;
+      const uint32_t bkt = min(h >> a.dirShift, 1023u);       // lower_bound of h in Q, inside its bucket
       int lo = tab[bkt], len = (int)tab[bkt + 1] - lo;
       while (len > 0) {
         const int half = len >> 1; const bool lt = Q[lo + half] < h;
         lo = lt ? lo + half + 1 : lo; len = lt ? len - half - 1 : half;
       }
-      const int j = lo;
-      const bool match = (j < s) && (Q[min(j, s - 1)] == h);
-      const bool m = eff && match, nm = eff && !match;
-      const uint32_t wi = (uint32_t)j >> 5, bit = 1u << (j & 31);
-      const uint32_t w = pres[wi];
-      if (m) pres[wi] = dir > 0 ? (w | bit) : (w & ~bit);
-      const uint32_t g = gap[j];
-      ovf |= nm && dir > 0 && g == 255u;
-      if (nm) gap[j] = (uint8_t)(g + dir);
-      const bool below = j < t;
-      P += (m && below) ? dir : 0;
-      G += (nm && below) ? dir : 0;
-      // the pivot t moves by at most one rank per update
-      const bool down = dir > 0 && (t + G > s);
-      const int tt = t - (down ? 1 : 0);
-      const int gv = gap[tt], pv = (int)((pres[tt >> 5] >> (tt & 31)) & 1u);
-      const bool up = dir < 0 && t < s && (t + 1 + G + gv <= s);
-      G += up ? gv : (down ? -gv : 0);
-      P += up ? pv : (down ? -pv : 0);
-      t += (up ? 1 : 0) - (down ? 1 : 0);
-    };
-    auto is_new = [](uint32_t link, uint32_t idx, uint32_t wb) { const uint32_t pd = link >> 16; return !(pd != 0xFFFFu && idx - pd >= wb); };
-    auto is_gone = [](uint32_t link, uint32_t idx, uint32_t we) { const uint32_t nd = link & 0xFFFFu; return !(nd != 0xFFFFu && idx + nd < we); };
-
-    if (act) {
-      const int seq = a.cSeq[c];
-      const uint32_t lo = a.contigRecOff[seq], hi = a.contigRecOff[seq + 1];
-      b = lb_rec(a.rec, lo, hi, a.cStart[c]);
-      e = lb_rec(a.rec, lo, hi, (int32_t)__ldg(&a.rec[b]).y + a.cmw);
-      last = lb_rec(a.rec, lo, hi, a.cEnd[c] + a.fragLen);
-    }
-    const uint32_t b0 = b;
-    // the first super-window
-    uint32_t r = b;
-    while (__any_sync(0xffffffffu, act && r < e && !ovf)) {
-      if (act && r < e && !ovf) { const uint4 rc = __ldg(&a.rec[r]); apply(rc.x, is_new(rc.z, r, b), +1); r++; }
-    }
-    // slide
-    int sw = 0, best = 0, first = 0, lastp = 0;
-    // both streams are read two records ahead so a load is never consumed in the iteration that issued it
-    uint4 cur = make_uint4(0, 0, 0, 0), nxt = cur, nxt2 = cur, re = cur, re2 = cur;
-    bool run = act && e < last && !ovf;
-    const uint32_t Mm1 = a.M - 1;
-    if (run) {
-      cur = __ldg(&a.rec[b]); nxt = __ldg(&a.rec[b + 1]); nxt2 = __ldg(&a.rec[min(b + 2, Mm1)]);
-      re = __ldg(&a.rec[e]); re2 = __ldg(&a.rec[min(e + 1, Mm1)]); sw = (int)cur.y;
-    }
-    while (__any_sync(0xffffffffu, run)) {
-      if (run) {
-        if (P > best) { best = P; first = lastp = (int)cur.y; }
-        else if (P == best) lastp = (int)cur.y;
-        const int d1 = (int)nxt.y - sw, d2 = (int)re.y - (sw + a.cmw - 1);
-        const int adv = min(d1, d2);
-        sw += adv;
-        const uint32_t ob = b, oe = e;
-        const bool doRem = adv == d1, doIns = adv == d2;
-        // the leaving record first (slidingMap.hpp order: delete_ref, then insert_ref); one uniform update
-        // per iteration, a second one only when both ends move together
-        apply(doRem ? cur.x : re.x, doRem ? is_gone(cur.z, ob, oe) : is_new(re.z, oe, ob), doRem ? -1 : +1);
-        if (doRem) { b++; cur = nxt; nxt = nxt2; nxt2 = __ldg(&a.rec[min(b + 2, Mm1)]); }
-        if (doRem && doIns) apply(re.x, is_new(re.z, oe, b), +1);
-        if (doIns) { e++; re = re2; re2 = __ldg(&a.rec[min(e + 1, Mm1)]); }
-        run = (e < last) && !ovf;
+      const uint32_t j = (uint32_t)lo;
+      const bool match = ((int)j < s) && (Q[min((int)j, s - 1)] == h);
+      // rank s (hashes above every query hash) never reaches the pivot: such events are no-ops
+      const uint32_t base = j | (match ? EV_M : 0u);
+      const bool can = (int)j < s;
+      const uint32_t pd = rc.z >> 16, nd = rc.z & 0xFFFFu, back = rc.w & 0xFFFFu, fwd = rc.w >> 16;
+      // this record ENTERS the window
+      uint32_t pos, wb; bool sc;
+      if (r < e0) { pos = r - b0; wb = b0; sc = (r == e0 - 1); }
+      else { wb = (back > r - b0) ? b0 : r - back; pos = nInit + (r - e0) + (wb - b0); sc = (r != last - 1); }
+      const bool isNew = !(pd != 0xFFFFu && r - pd >= wb);     // no earlier twin inside the window
+      ev[pos] = (uint16_t)(base | EV_D | ((can && isNew) ? EV_E : 0u) | (sc ? EV_S : 0u));
+      // this record LEAVES the window (only if that happens no later than the step in which last-1 enters)
+      if (fwd != 0xFFFFu && r + fwd <= last - 1) {
+        const uint32_t we = r + fwd;
+        const bool gone = !(nd != 0xFFFFu && r + nd < we);     // no later twin still inside the window
+        const uint32_t posr = nInit + (r - b0) + (we - e0);
+        ev[posr] = (uint16_t)(base | ((can && gone) ? EV_E : 0u) | ((rc.y >> 31) ? 0u : EV_S));
       }
     }
-    if (act) {
-      if (ovf) a.cBest[c] = -1;
-      else { a.cPos[c] = (first + lastp) / 2; a.cBest[c] = best; n2 += last - b0; }
-    }
-    __syncwarp();
   }
-  for (int o = 16; o; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
-  if (lane == 0 && n2) atomicAdd(a.ctr_n2, n2);
+}
+
+static constexpr int L2S_WARPS = 4;
+
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(addr), "r"(v) : "memory"); }
+
+__global__ void __launch_bounds__(L2S_WARPS * 32)
+l2_seq_kernel(const L2PArgs a)
+{
+  extern __shared__ __align__(16) uint32_t smem[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint32_t gid = blockIdx.x * (L2S_WARPS * 32) + threadIdx.x;
+  // word i of this lane's state lives at warpBase + i*32 + lane: bank == lane for every access
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem) + ((uint32_t)wid * a.laneWords * 32u + (uint32_t)lane) * 4u;
+  const uint32_t pbase = sbase + a.gapWords * 128u;
+  for (uint32_t i = 0; i < a.laneWords; i++) sts_u32(sbase + i * 128u, 0u);
+
+  uint32_t c = 0, nEv = 0; int s = 1;
+  if (gid < a.C) { c = a.perm[gid]; nEv = a.cNEv[c]; s = a.sCount[a.cFrag[c]]; }
+  const uint4 *strm = reinterpret_cast<const uint4 *>(a.events) + (nEv ? a.cOff[c] : 0u);
+  const uint32_t nCh = (nEv + 7) >> 3;
+  uint32_t maxCh = nCh;
+  for (int o = 16; o; o >>= 1) maxCh = max(maxCh, __shfl_xor_sync(0xffffffffu, maxCh, o));
+
+  int t = s, G = 0, P = 0, best = 0;
+  uint32_t nrem = 0, firstN = 0, lastN = 0, ovf = 0;
+  uint4 nxt = make_uint4(0, 0, 0, 0);
+  if (nCh) nxt = __ldg(strm);
+  for (uint32_t ch = 0; ch < maxCh; ch++) {
+    const uint4 cur = nxt;
+    if (ch + 1 < nCh) nxt = __ldg(strm + ch + 1);
+    const uint32_t wv[4] = {cur.x, cur.y, cur.z, cur.w};
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      uint32_t ev = (q & 1) ? (wv[q >> 1] >> 16) : (wv[q >> 1] & 0xFFFFu);
+      const bool valid = ch * 8 + q < nEv;
+      ev = valid ? ev : 0u;
+      const uint32_t j = ev & L2_JMASK;
+      const bool ins = ev & EV_D, eff = ev & EV_E;
+      const bool m = eff && (ev & EV_M), nm = eff && !(ev & EV_M);
+      const int dir = ins ? 1 : -1;
+      const uint32_t ga = sbase + (j >> 2) * 128u + (j & 3u);
+      const uint32_t pa = pbase + (j >> 5) * 128u;
+      const uint32_t g = lds_u8(ga);
+      const uint32_t pw = lds_u32(pa);
+      ovf |= (nm && ins && g == 255u) ? 1u : 0u;
+      if (nm) sts_u8(ga, g + dir);
+      if (m) sts_u32(pa, pw ^ (1u << (j & 31u)));
+      const bool below = (int)j < t;
+      P += (m && below) ? dir : 0;
+      G += (nm && below) ? dir : 0;
+      // the pivot moves by at most one rank per event (down only after an insert, up only after a removal)
+      const bool down = t + G > s;
+      const int tt = t - (down ? 1 : 0);
+      const int gv = (int)lds_u8(sbase + ((uint32_t)tt >> 2) * 128u + ((uint32_t)tt & 3u));
+      const int pv = (int)((lds_u32(pbase + ((uint32_t)tt >> 5) * 128u) >> (tt & 31)) & 1u);
+      const bool up = !down && t < s && (t + 1 + G + gv <= s);
+      G += up ? gv : (down ? -gv : 0);
+      P += up ? pv : (down ? -pv : 0);
+      t = tt + (up ? 1 : 0);
+      nrem += (valid && !ins) ? 1u : 0u;
+      if (ev & EV_S) {
+        if (P > best) { best = P; firstN = nrem; lastN = nrem; }
+        else if (P == best) lastN = nrem;
+      }
+    }
+  }
+  if (gid < a.C && nEv) {
+    if (ovf) a.cBest[c] = -1;
+    else {
+      const uint32_t b0 = a.cB0[c];
+      const int first = best > 0 ? rec_wpos(a.rec, b0 + firstN) : 0;   // "first" stays 0 while best == 0 (as in the sweep above)
+      const int lastp = rec_wpos(a.rec, b0 + lastN);
+      a.cPos[c] = (first + lastp) / 2;
+      a.cBest[c] = best;
+    }
+  }
 }
 
 // ------------------------------------------------------------------ G: report
@@ -688,33 +763,65 @@ void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_
             BANI_SCRATCH(uint8_t, scratch, (size_t)blocks * 64 * l2.stride);
             BANI_SCRATCH(unsigned long long, d_n2, 1);
             BANI_CUDA(cudaMemsetAsync(d_n2.p, 0, 8, st));
-            l2.scratch = scratch.p; l2.cPos = cPos.p; l2.cBest = cBest.p; l2.ctr_n2 = d_n2.p; l2.onlyFlagged = 1;
+            l2.scratch = scratch.p; l2.cPos = cPos.p; l2.cBest = cBest.p; l2.onlyFlagged = 1;
             {
               Stage sg(ctx, "l2");
-              // fast path: one warp per fragment, window state in shared memory
               BANI_SCRATCH(uint32_t, fragCandOff, (size_t)F + 1);
               frag_cand_off_kernel<<<nblk((uint64_t)F + 1), 256, 0, st>>>(cFrag.p, C, F, fragCandOff.p);
               ctx->launches++;
-              L2WArgs lw; lw.cSeq = cSeq.p; lw.cStart = cStart.p; lw.cEnd = cEnd.p; lw.fragCandOff = fragCandOff.p;
-              lw.fragHash = fragHash.p; lw.segStart = segStart.p; lw.sCount = sCount.p;
-              lw.rec = ix->rec.p; lw.contigRecOff = ix->contigRecOff.p; lw.M = (uint32_t)ix->M;
-              lw.fragLen = fragLen; lw.cmw = cmw;
-              lw.sLimit = std::min(smax, 1024);
-              lw.gapWords = (uint32_t)(lw.sLimit + 1 + 3) / 4;
-              lw.strideWords = (lw.gapWords + (uint32_t)(lw.sLimit + 32) / 32) | 1u;      // odd => conflict-free lanes
-              lw.cPos = cPos.p; lw.cBest = cBest.p; lw.ctr_n2 = d_n2.p;
-              const size_t shm = 4 * ((size_t)lw.sLimit + 516 + 32 * (size_t)lw.strideWords);
-              static bool attrSet = false;
-              if (!attrSet) {
-                BANI_CUDA(cudaFuncSetAttribute(l2_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                // shared-memory carve-out: occupancy (window state per lane) beats L1 capacity here (measured 25/50/75/100 %)
-                // and re-use each 128-byte line eight times
-                int carve = 100; if (const char *ev = getenv("BANI_L2_CARVEOUT")) carve = atoi(ev);
-                BANI_CUDA(cudaFuncSetAttribute(l2_warp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-                attrSet = true;
+              L2PArgs lp; lp.cFrag = cFrag.p; lp.cSeq = cSeq.p; lp.cStart = cStart.p; lp.cEnd = cEnd.p; lp.C = C;
+              lp.fragCandOff = fragCandOff.p; lp.fragHash = fragHash.p; lp.segStart = segStart.p; lp.sCount = sCount.p;
+              lp.rec = ix->rec.p; lp.contigRecOff = ix->contigRecOff.p; lp.fragLen = fragLen; lp.cmw = cmw;
+              // fast path: needs the window links of the index (cmw >= 2) and ranks that fit the event code
+              lp.sLimit = (cmw >= 2 && ix->cmw == cmw) ? std::min(smax, L2_JMASK) : 0;
+              { int lg = 0; while ((8 << (lg + 1)) <= w + 1) lg++; lp.dirShift = std::max(22 - lg, 10); }   // hashes of minimizers crowd below 2^32 * c/(w+1)
+              lp.gapWords = (uint32_t)(std::max(lp.sLimit, 1) + 1 + 3) / 4;
+              lp.laneWords = lp.gapWords + (uint32_t)(std::max(lp.sLimit, 1) >> 5) + 1;
+              BANI_SCRATCH(uint32_t, cB0, C);          // (one scratch slot per source line)
+              BANI_SCRATCH(uint32_t, cE0, C);
+              BANI_SCRATCH(uint32_t, cLast, C);
+              BANI_SCRATCH(uint32_t, cNEv, C);
+              BANI_SCRATCH(uint32_t, cChunks, (size_t)C + 1);
+              BANI_SCRATCH(uint32_t, cOff, (size_t)C + 1);
+              lp.cB0 = cB0.p; lp.cE0 = cE0.p; lp.cLast = cLast.p; lp.cNEv = cNEv.p; lp.cChunks = cChunks.p; lp.cOff = cOff.p;
+              lp.cPos = cPos.p; lp.cBest = cBest.p; lp.ctr_n2 = d_n2.p; lp.events = nullptr; lp.perm = nullptr;
+              l2_bounds_kernel<<<nblk((uint64_t)C + 1), 256, 0, st>>>(lp); ctx->launches++;
+              if (lp.sLimit > 0) {
+                { size_t tb = cub_scan_u64_temp((size_t)C + 1);
+                  BANI_SCRATCH(uint8_t, tmp, tb);
+                  BANI_SCRATCH(unsigned long long, cOff64, (size_t)C + 1);
+                  cub_exclusive_sum_u32_to_u64(tmp.p, tb, cChunks.p, (uint64_t *)cOff64.p, (size_t)C + 1, st);
+                  unsigned long long totalChunks = 0;
+                  BANI_CUDA(cudaMemcpyAsync(&totalChunks, cOff64.p + C, 8, cudaMemcpyDeviceToHost, st));
+                  BANI_CUDA(cudaStreamSynchronize(st));
+                  if (totalChunks > 0xfffffff0ull) fail(BANI_ERR_LIMIT, "query chunk schedules more than 2^35 window events");
+                  tb = cub_scan_u32_temp((size_t)C + 1);
+                  BANI_SCRATCH(uint8_t, tmp2, tb);
+                  cub_exclusive_sum_u32(tmp2.p, tb, cChunks.p, cOff.p, (size_t)C + 1, st);
+                  BANI_SCRATCH(uint16_t, events, (size_t)totalChunks * 8 + 64);
+                  lp.events = events.p; }
+                BANI_SCRATCH(uint32_t, skey, C);
+                BANI_SCRATCH(uint32_t, skey2, C);
+                BANI_SCRATCH(uint32_t, sval, C);
+                BANI_SCRATCH(uint32_t, perm, C);
+                l2_sortkey_kernel<<<nblk(C), 256, 0, st>>>(cNEv.p, C, skey.p, sval.p); ctx->launches++;
+                { size_t tb = cub_sort_pairs_u32_temp(C);
+                  BANI_SCRATCH(uint8_t, tmp, tb);
+                  cub_sort_pairs_u32(tmp.p, tb, skey.p, skey2.p, sval.p, perm.p, C, 20, st); }
+                lp.perm = perm.p;
+                static bool attrSet = false;
+                const size_t shmE = 4 * (size_t)lp.sLimit + 2 * 1026 + 16;
+                const size_t shmS = 4 * (size_t)L2S_WARPS * 32 * lp.laneWords;
+                if (shmE > 200 * 1024 || shmS > 200 * 1024) fail(BANI_ERR_INTERNAL, "L2 shared-memory budget exceeded");
+                if (!attrSet) {
+                  BANI_CUDA(cudaFuncSetAttribute(l2_events_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                  BANI_CUDA(cudaFuncSetAttribute(l2_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                  BANI_CUDA(cudaFuncSetAttribute(l2_seq_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+                  attrSet = true;
+                }
+                l2_events_kernel<<<F, L2E_THREADS, shmE, st>>>(lp); ctx->launches++;
+                l2_seq_kernel<<<nblk(C, L2S_WARPS * 32), L2S_WARPS * 32, shmS, st>>>(lp); ctx->launches++;
               }
-              l2_warp_kernel<<<F, 32, shm, st>>>(lw);
-              ctx->launches++;
               // exact slow path for whatever the fast path flagged (uint8 counter overflow, very large sketches)
               l2_kernel<<<blocks, 64, 0, st>>>(l2); ctx->launches++;
             }
