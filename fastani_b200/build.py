@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "lib")
 LIB = os.path.join(OUT, "libfastani_b200.so")
-SOURCES = ["capi.cu", "pack.cu", "sketch.cu", "index.cu", "map.cu", "synth.cu", "cubops.cu", "stats.cpp", "alloc.cpp"]
+SOURCES = ["capi.cu", "pack.cu", "sketch.cu", "index.cu", "map.cu", "hits.cu", "synth.cu", "cubops.cu", "stats.cpp", "alloc.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr", "-x", "cu"]

@@ -158,7 +158,12 @@ struct Ctx {
     View<T> v; v.p = (T *)b.p; v.n = n; return v;
   }
 };
-#define BANI_SCRATCH(T, name, count) ::bani::View<T> name = ctx->view<T>(__LINE__, (count))
+#ifndef BANI_FILE_TAG
+#define BANI_FILE_TAG 0
+#endif
+// one scratch slot per (source file, source line): never put two BANI_SCRATCH on one line
+#define BANI_SLOT_ID ((BANI_FILE_TAG << 20) | __LINE__)
+#define BANI_SCRATCH(T, name, count) ::bani::View<T> name = ctx->view<T>(BANI_SLOT_ID, (count))
 
 // RAII stage timer: records an event pair around a stage when profiling is on.
 struct Stage {
@@ -201,6 +206,26 @@ struct MapOutput {
 };
 void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_t nq,
                  bool wantRows, bool wantCgi, MapOutput &out);
+
+// hits.cu : per-fragment gather + shared-memory sort + L1 candidate regions
+static constexpr unsigned long long FRAG_L1_MAX = 8192;   // hits per fragment handled inside one CTA
+struct FragL1Args {
+  const uint32_t *segStart; const int32_t *sCount; int32_t F;
+  const uint32_t *hitLo, *hitCnt; const unsigned long long *hitOff;
+  const uint32_t *posIdx; const int32_t *recSeq, *recWpos;
+  const int32_t *minHits; int fragLen, keyBits;
+  int32_t *stSeq, *stStart, *stEnd;      // staging, addressed by global hit offset
+  uint32_t *candCount;                   // per fragment
+};
+void frag_classify(Ctx *ctx, const uint32_t *segStart, const unsigned long long *hitOff, int32_t F,
+                   uint32_t *candCount, uint32_t *fragClass, uint32_t *classCount, uint32_t *classList, unsigned long long maxFast);
+void frag_l1_fast(Ctx *ctx, const FragL1Args &a, const uint32_t *classList, const uint32_t classCount[4]);
+void cand_stage(Ctx *ctx, const int32_t *cFrag, const int32_t *cSeq, const int32_t *cStart, const int32_t *cEnd, uint32_t C,
+                const uint32_t *segStart, const unsigned long long *hitOff, int32_t *stSeq, int32_t *stStart, int32_t *stEnd,
+                uint32_t *candCount);
+void cand_compact(Ctx *ctx, const uint32_t *segStart, const unsigned long long *hitOff, int32_t F,
+                  const uint32_t *candCount, const uint32_t *candOff, const int32_t *stSeq, const int32_t *stStart,
+                  const int32_t *stEnd, int32_t *cFrag, int32_t *cSeq, int32_t *cStart, int32_t *cEnd);
 
 // synth.cu
 void synth_genome(Ctx *ctx, uint64_t seed, uint32_t ancestor, uint32_t strain, uint32_t ppm,

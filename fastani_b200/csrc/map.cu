@@ -120,7 +120,16 @@ __global__ void gather_kernel(const uint32_t *segStart, int32_t F, uint32_t T, c
   for (uint32_t j = 0; j < cnt; j++) keys[o + j] = (f << 32) | posIdx[lo + j];
 }
 
-// ------------------------------------------------------------------ E: L1 candidate regions
+// hit counts of the fragments left to the device-wide path (class 4), zero for everything else
+__global__ void mask_hits_kernel(const uint32_t *segStart, int32_t F, uint32_t T, const uint32_t *hitCnt, const uint32_t *fragClass,
+                                 uint32_t *bigCnt)
+{
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > T) return;
+  bigCnt[t] = (t < T && fragClass[seg_of(segStart, F, t)] == 4u) ? hitCnt[t] : 0u;
+}
+
+// ------------------------------------------------------------------ E: L1 candidate regions (device-wide path)
 struct L1Args {
   const unsigned long long *keys; unsigned long long N;
   const uint32_t *segStart; const unsigned long long *hitOff; const int32_t *sCount;
@@ -714,31 +723,78 @@ void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_
         if (N > 0xfffffff0ull) fail(BANI_ERR_LIMIT, "query chunk gathers more than 2^32 index hits");
 
         if (N > 0) {
-          // ---- D: gather + sort
-          BANI_SCRATCH(unsigned long long, keysA, N);
-          BANI_SCRATCH(unsigned long long, keysB, N);
-          { Stage sg(ctx, "hit_gather", 12.0 * N);
-            gather_kernel<<<nblk(T), 256, 0, st>>>(segStart.p, F, (uint32_t)T, hitLo.p, hitCnt.p, hitOff.p, ix->posIdx.p, keysA.p); ctx->launches++; }
-          int fbits = 1; while ((1ll << fbits) < F) fbits++;
-          { Stage sg(ctx, "hit_sort", 16.0 * N);
-            size_t tb = cub_sort_keys_u64_temp(N);
+          // ---- D+E: hits -> L1 candidate regions.  Fragments with at most FRAG_L1_MAX hits are handled by
+          //      one CTA each (hits.cu); the others go through the device-wide sort below.  Both write their
+          //      regions to a staging area addressed by the fragment's hit offset; a scan + copy makes them dense.
+          BANI_SCRATCH(uint32_t, candCount, (size_t)F + 1);
+          BANI_SCRATCH(uint32_t, candOff, (size_t)F + 1);
+          BANI_SCRATCH(uint32_t, fragClass, F);
+          BANI_SCRATCH(uint32_t, classList, (size_t)4 * F);
+          BANI_SCRATCH(uint32_t, classCount, 8);
+          BANI_SCRATCH(int32_t, stSeq, N);
+          BANI_SCRATCH(int32_t, stStart, N);
+          BANI_SCRATCH(int32_t, stEnd, N);
+          static const long long maxFast = [] { const char *e = getenv("BANI_FRAG_L1_MAX"); long long v = e ? atoll(e) : (long long)FRAG_L1_MAX;
+                                                return std::max(0ll, std::min(v, (long long)FRAG_L1_MAX)); }();
+          uint32_t hClass[8];
+          { Stage sg(ctx, "frag_l1", 12.0 * N);
+            frag_classify(ctx, segStart.p, hitOff.p, F, candCount.p, fragClass.p, classCount.p, classList.p, (unsigned long long)maxFast);
+            BANI_CUDA(cudaMemcpyAsync(hClass, classCount.p, sizeof hClass, cudaMemcpyDeviceToHost, st));
+            BANI_CUDA(cudaStreamSynchronize(st));
+            FragL1Args fa; fa.segStart = segStart.p; fa.sCount = sCount.p; fa.F = F; fa.hitLo = hitLo.p; fa.hitCnt = hitCnt.p; fa.hitOff = hitOff.p;
+            fa.posIdx = ix->posIdx.p; fa.recSeq = ix->seqId.p; fa.recWpos = ix->wpos.p; fa.minHits = ctx->d_minHits.p; fa.fragLen = fragLen;
+            fa.keyBits = 1; while (fa.keyBits < 32 && (1ull << fa.keyBits) < ix->M) fa.keyBits++;
+            fa.stSeq = stSeq.p; fa.stStart = stStart.p; fa.stEnd = stEnd.p; fa.candCount = candCount.p;
+            frag_l1_fast(ctx, fa, classList.p, hClass); }
+          if (hClass[4] > 0) {
+            // ---- device-wide path for the oversized fragments: (fragment, record) keys, one radix sort, flags + scan + write
+            BANI_SCRATCH(uint32_t, bigCnt, T + 1);
+            BANI_SCRATCH(unsigned long long, bigOff, T + 1);
+            mask_hits_kernel<<<nblk(T + 1), 256, 0, st>>>(segStart.p, F, (uint32_t)T, hitCnt.p, fragClass.p, bigCnt.p); ctx->launches++;
+            { size_t tb = cub_scan_u64_temp(T + 1);
+              BANI_SCRATCH(uint8_t, tmp, tb);
+              cub_exclusive_sum_u32_to_u64(tmp.p, tb, bigCnt.p, (uint64_t *)bigOff.p, T + 1, st); }
+            unsigned long long NB = 0;
+            BANI_CUDA(cudaMemcpyAsync(&NB, bigOff.p + T, 8, cudaMemcpyDeviceToHost, st));
+            BANI_CUDA(cudaStreamSynchronize(st));
+            BANI_SCRATCH(unsigned long long, keysA, NB);
+            BANI_SCRATCH(unsigned long long, keysB, NB);
+            { Stage sg(ctx, "hit_gather", 12.0 * NB);
+              gather_kernel<<<nblk(T), 256, 0, st>>>(segStart.p, F, (uint32_t)T, hitLo.p, bigCnt.p, bigOff.p, ix->posIdx.p, keysA.p); ctx->launches++; }
+            int fbits = 1; while ((1ll << fbits) < F) fbits++;
+            { Stage sg(ctx, "hit_sort", 16.0 * NB);
+              size_t tb = cub_sort_keys_u64_temp(NB);
+              BANI_SCRATCH(uint8_t, tmp, tb);
+              cub_sort_keys_u64(tmp.p, tb, (const uint64_t *)keysA.p, (uint64_t *)keysB.p, NB, 0, 32 + fbits, st); }
+            L1Args la; la.keys = keysB.p; la.N = NB; la.segStart = segStart.p; la.hitOff = bigOff.p; la.sCount = sCount.p;
+            la.minHits = ctx->d_minHits.p; la.recSeq = ix->seqId.p; la.recWpos = ix->wpos.p; la.fragLen = fragLen;
+            BANI_SCRATCH(uint32_t, head, NB + 1);
+            BANI_SCRATCH(uint32_t, headScan, NB + 1);
+            { Stage sg(ctx, "l1_flags", 8.0 * NB);
+              l1_flag_kernel<<<nblk(NB + 1), 256, 0, st>>>(la, head.p);
+              ctx->launches++;
+              size_t tb = cub_scan_u32_temp(NB + 1);
+              BANI_SCRATCH(uint8_t, tmp, tb);
+              cub_exclusive_sum_u32(tmp.p, tb, head.p, headScan.p, NB + 1, st); }
+            uint32_t CB = 0;
+            BANI_CUDA(cudaMemcpyAsync(&CB, headScan.p + NB, 4, cudaMemcpyDeviceToHost, st));
+            BANI_CUDA(cudaStreamSynchronize(st));
+            if (CB > 0) {
+              BANI_SCRATCH(int32_t, bFrag, CB);
+              BANI_SCRATCH(int32_t, bSeq, CB);
+              BANI_SCRATCH(int32_t, bStart, CB);
+              BANI_SCRATCH(int32_t, bEnd, CB);
+              Stage sg(ctx, "l1_write", 8.0 * NB);
+              l1_write_kernel<<<nblk(NB), 256, 0, st>>>(la, head.p, headScan.p, bFrag.p, bSeq.p, bStart.p, bEnd.p); ctx->launches++;
+              cand_stage(ctx, bFrag.p, bSeq.p, bStart.p, bEnd.p, CB, segStart.p, hitOff.p, stSeq.p, stStart.p, stEnd.p, candCount.p);
+            }
+          }
+          { size_t tb = cub_scan_u32_temp((size_t)F + 1);
             BANI_SCRATCH(uint8_t, tmp, tb);
-            cub_sort_keys_u64(tmp.p, tb, (const uint64_t *)keysA.p, (uint64_t *)keysB.p, N, 0, 32 + fbits, st); }
-          keysA.release();
-
-          // ---- E: L1 candidate regions
-          L1Args la; la.keys = keysB.p; la.N = N; la.segStart = segStart.p; la.hitOff = hitOff.p; la.sCount = sCount.p;
-          la.minHits = ctx->d_minHits.p; la.recSeq = ix->seqId.p; la.recWpos = ix->wpos.p; la.fragLen = fragLen;
-          BANI_SCRATCH(uint32_t, head, N + 1);
-          BANI_SCRATCH(uint32_t, headScan, N + 1);
-          { Stage sg(ctx, "l1_flags", 8.0 * N);
-            l1_flag_kernel<<<nblk(N + 1), 256, 0, st>>>(la, head.p);
-            ctx->launches++;
-            size_t tb = cub_scan_u32_temp(N + 1);
-            BANI_SCRATCH(uint8_t, tmp, tb);
-            cub_exclusive_sum_u32(tmp.p, tb, head.p, headScan.p, N + 1, st); }
+            BANI_CUDA(cudaMemsetAsync(candCount.p + F, 0, 4, st));
+            cub_exclusive_sum_u32(tmp.p, tb, candCount.p, candOff.p, (size_t)F + 1, st); }
           uint32_t C = 0;
-          BANI_CUDA(cudaMemcpyAsync(&C, headScan.p + N, 4, cudaMemcpyDeviceToHost, st));
+          BANI_CUDA(cudaMemcpyAsync(&C, candOff.p + F, 4, cudaMemcpyDeviceToHost, st));
           BANI_CUDA(cudaStreamSynchronize(st));
           out.ctr.candidates += C;
 
@@ -749,9 +805,7 @@ void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_
             BANI_SCRATCH(int32_t, cEnd, C);
             BANI_SCRATCH(int32_t, cPos, C);
             BANI_SCRATCH(int32_t, cBest, C);
-            { Stage sg(ctx, "l1_write", 8.0 * N);
-              l1_write_kernel<<<nblk(N), 256, 0, st>>>(la, head.p, headScan.p, cFrag.p, cSeq.p, cStart.p, cEnd.p); ctx->launches++; }
-            head.release(); headScan.release(); keysB.release();
+            cand_compact(ctx, segStart.p, hitOff.p, F, candCount.p, candOff.p, stSeq.p, stStart.p, stEnd.p, cFrag.p, cSeq.p, cStart.p, cEnd.p);
 
             // ---- F: L2
             L2Args l2; l2.cFrag = cFrag.p; l2.cSeq = cSeq.p; l2.cStart = cStart.p; l2.cEnd = cEnd.p; l2.C = C;

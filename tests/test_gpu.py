@@ -223,3 +223,33 @@ def test_device_synth_matches_numpy_twin():
 def test_smoke_entry():
     import __graft_entry__ as g
     g.smoke()
+
+
+_PATH_SCRIPT = r"""
+import hashlib, os, sys
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+import fastani_b200 as fb
+G = os.path.join(sys.argv[1], "tests", "golden")
+ec = fb.read_fasta(os.path.join(G, "Escherichia_coli_str_K12_MG1655.fna.gz"))
+sh = fb.read_fasta(os.path.join(G, "Shigella_flexneri_2a_01.fna.gz"))
+ctx = fb.Context(fb.Parameters())
+ge, gs = ctx.genomes([ec, sh])
+sk = fb.Sketch(ctx, [ge, gs])
+for q in (gs, ge):
+    m = fb.Map(ctx, sk, q)
+    print(len(m.rows), hashlib.sha256(m.rows.tobytes()).hexdigest(), m.counters.as_dict()["candidates"])
+"""
+
+
+def test_hit_paths_agree():
+    """The per-fragment shared-memory path (hits.cu), the device-wide sort path and their mix give the same rows."""
+    import subprocess, sys
+    from conftest import ROOT
+    outs = []
+    for cap in ("8192", "0", "300", "1500"):           # all fast / all device-wide / two different mixes
+        env = dict(os.environ, BANI_FRAG_L1_MAX=cap)
+        r = subprocess.run([sys.executable, "-c", _PATH_SCRIPT, ROOT], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(r.stdout)
+    assert outs[0] == outs[1] == outs[2] == outs[3] and outs[0].count("\n") == 2
