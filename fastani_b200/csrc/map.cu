@@ -280,31 +280,38 @@ l2_kernel(const L2Args a)
 // the sweep state can be computed for all (candidate, record) pairs in parallel:
 //   l2_bounds_kernel  lane per candidate: b0 / e0 / last (the three lower_bounds of computeMap.hpp:424-436) and
 //                     the exact number of window events
-//   l2_events_kernel  CTA per fragment (its sketch Q + a bucket directory in shared memory), lane per record:
-//                     rank of the record's hash in Q, match bit, and -- from the per-record window links
+//   l2_events_kernel  CTA per fragment (its sketch Q + a two-level bucket directory in shared memory), lane per
+//                     record: rank of the record's hash in Q, match bit, and -- from the per-record window links
 //                     back / fwd / tie stored in the index (index.cu) -- the exact position of its "enters"
 //                     and "leaves" events in the candidate's event stream, whether the event changes the set of
 //                     DISTINCT window hashes (twin links), and whether a scoring point follows it.
-//                     One 16-bit code per event: j[0:10] | match<<11 | insert<<12 | effective<<13 | score<<14.
 //   l2_seq_kernel     lane per candidate (candidates ordered by event count so a warp's lanes finish together):
-//                     streams the 16-bit codes (16-byte loads, one ahead) through the rank-space window state
-//                     (gap[] uint8 + pres bitmap per lane in shared memory, word-interleaved across lanes so that
-//                     every access is bank-conflict free whatever the ranks are).
-// Counter overflow (255 distinct foreign hashes between two neighbouring query hashes) or s > 2047 hands the
-// candidate to the exact global-memory kernel above.
-static constexpr int L2_JBITS = 11, L2_JMASK = (1 << L2_JBITS) - 1;
-static constexpr uint32_t EV_M = 1u << 11, EV_D = 1u << 12, EV_E = 1u << 13, EV_S = 1u << 14;
+//                     streams the 16-bit codes (16-byte loads, one ahead) through the rank-space window state.
+//
+// Window state: ONE byte per rank j in shared memory = (number of distinct window hashes that are not in Q and
+// have exactly j query hashes below them) | (q_j present in the window) << 7.  Byte j of a lane lives at
+// j * 32 + lane of its warp's region, so the offset of a rank is the rank shifted: no address arithmetic, at the
+// price of ~2-way bank conflicts (the four lanes that share a 32-bit word column).
+//
+// Event code (16 bits):  match [0] | insert [1] | score-after [2] | j [5:15]
+// so that (code & 0xFFE0) is the byte offset of rank j and compares like j.  Events that do not change the set of
+// distinct window hashes (a twin is inside the window), and events of hashes above every query hash, are coded as
+// a "match" at rank s: they toggle the presence bit of the sentinel rank s, which no pivot position ever counts.
+// A count reaching 64 (or s > 2047) hands the candidate to the exact global-memory kernel above.
+static constexpr int L2_SMAX = 2047;
+static constexpr uint32_t EV_M = 1u, EV_D = 2u, EV_S = 4u, EV_JMASK = 0xFFE0u;
+__host__ __device__ __forceinline__ uint32_t ev_rank(uint32_t j) { return j << 5; }
 
 struct L2PArgs {
   const int32_t *cFrag, *cSeq, *cStart, *cEnd; uint32_t C;
   const uint32_t *fragCandOff;
   const uint32_t *fragHash; const uint32_t *segStart; const int32_t *sCount;
   const uint4 *rec; const uint32_t *contigRecOff;
-  int fragLen, cmw, sLimit, dirShift;
+  int fragLen, cmw, sLimit, shiftA;
   uint32_t *cB0, *cE0, *cLast, *cNEv, *cChunks;   // per candidate
-  const uint32_t *cOff;                            // stream offset in 16-byte units
+  const uint32_t *cOff;                            // stream offset in 32-byte units (16 events)
   uint16_t *events;
-  const uint32_t *perm; uint32_t gapWords, laneWords;
+  const uint32_t *perm; uint32_t warpBytes;
   int32_t *cPos, *cBest; unsigned long long *ctr_n2;
 };
 
@@ -344,10 +351,10 @@ __global__ void l2_bounds_kernel(const L2PArgs a)
       nEv = (e0 - b0) + (last - e0) + (bEnd - b0);
     }
     a.cB0[c] = b0; a.cE0[c] = e0; a.cLast[c] = last;
-    const bool fast = s >= 1 && s <= a.sLimit;
+    const bool fast = s >= 1 && s <= a.sLimit && nEv < (1u << 20);
     a.cNEv[c] = fast ? nEv : 0u;
-    a.cChunks[c] = fast ? (nEv + 7) >> 3 : 0u;
-    a.cBest[c] = fast ? 0 : -1;                 // -1: exact slow kernel
+    a.cChunks[c] = fast ? (nEv + 15) >> 4 : 0u;      // 32-byte steps of 16 events
+    a.cBest[c] = (fast || nEv == 0) ? 0 : -1;   // -1: exact slow kernel
     a.cPos[c] = 0;
   } else if (c == a.C) a.cChunks[c] = 0;
   for (int o = 16; o; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
@@ -363,6 +370,13 @@ __global__ void l2_sortkey_kernel(const uint32_t *cNEv, uint32_t C, uint32_t *ke
 }
 
 static constexpr int L2E_THREADS = 256;
+static constexpr int L2E_TAB = 2048;             // buckets: [0,1024) width 2^shiftA from 0; [1024,2048) width 2^22 over the whole range
+
+__device__ __forceinline__ uint32_t l2e_bucket(uint32_t h, int shiftA)
+{
+  const uint32_t a = h >> shiftA;
+  return a < 1024u ? a : 1024u + (h >> 22);
+}
 
 __global__ void __launch_bounds__(L2E_THREADS)
 l2_events_kernel(const L2PArgs a)
@@ -373,52 +387,68 @@ l2_events_kernel(const L2PArgs a)
   if (c0 == c1) return;
   const int s = a.sCount[f];
   if (s < 1 || s > a.sLimit) return;
-  uint32_t *Q = smem;                                          // sLimit words
-  uint16_t *tab = (uint16_t *)(smem + a.sLimit);               // 1025 entries
+  uint32_t *Q = smem;                                          // sLimit + 3 words (3 probes past the end read the pad)
+  uint16_t *tab = (uint16_t *)(smem + a.sLimit + 4);           // L2E_TAB + 1 entries
   {
     const uint32_t *Qg = a.fragHash + a.segStart[f];
-    for (int i = tid; i < s; i += L2E_THREADS) Q[i] = Qg[i];
+    for (int i = tid; i < s + 3; i += L2E_THREADS) Q[i] = i < s ? Qg[i] : 0xFFFFFFFFu;
     __syncthreads();
-    for (int bkt = tid; bkt <= 1024; bkt += L2E_THREADS) {
+    const uint32_t split = a.shiftA + 10 >= 32 ? 0xFFFFFFFFu : (1024u << a.shiftA);
+    for (int bkt = tid; bkt <= L2E_TAB; bkt += L2E_THREADS) {
       int lo = 0, hi = s;
-      if (bkt == 1024) lo = s;
-      else { const uint32_t v = (uint32_t)bkt << a.dirShift; while (lo < hi) { int mid = (lo + hi) >> 1; if (Q[mid] < v) lo = mid + 1; else hi = mid; } }
+      if (bkt == L2E_TAB) lo = s;
+      else {
+        // lowest hash of the bucket
+        const uint32_t v = bkt < 1024 ? ((uint32_t)bkt << a.shiftA) : max((uint32_t)(bkt - 1024) << 22, split);
+        if (bkt < 1024 && ((uint64_t)bkt << a.shiftA) > 0xFFFFFFFFull) lo = s;
+        else while (lo < hi) { int mid = (lo + hi) >> 1; if (Q[mid] < v) lo = mid + 1; else hi = mid; }
+      }
       tab[bkt] = (uint16_t)lo;
     }
     __syncthreads();
   }
+  const uint32_t nop = ev_rank((uint32_t)s) | EV_M | EV_D;
   for (uint32_t c = c0 + wid; c < c1; c += L2E_THREADS / 32) {
     const uint32_t nEv = a.cNEv[c];
     if (nEv == 0) continue;
     const uint32_t b0 = a.cB0[c], e0 = a.cE0[c], last = a.cLast[c], nInit = e0 - b0;
-    uint16_t *ev = a.events + (size_t)a.cOff[c] * 8;
-    for (uint32_t r = b0 + lane; r < last; r += 32) {
-      const uint4 rc = __ldg(&a.rec[r]);
+    uint16_t *ev = a.events + (size_t)a.cOff[c] * 16;
+    if (lane < ((16u - (nEv & 15u)) & 15u)) ev[nEv + lane] = (uint16_t)nop;    // pad the last 32-byte step
+    uint32_t r = b0 + lane;
+    uint4 nxt = make_uint4(0, 0, 0, 0);
+    if (r < last) nxt = __ldg(&a.rec[r]);
+    for (; r < last; r += 32) {
+      const uint4 rc = nxt;
+      if (r + 32 < last) nxt = __ldg(&a.rec[r + 32]);
       const uint32_t h = rc.x;
-      const uint32_t bkt = min(h >> a.dirShift, 1023u);       // lower_bound of h in Q, inside its bucket
-      int lo = tab[bkt], len = (int)tab[bkt + 1] - lo;
-      while (len > 0) {
-        const int half = len >> 1; const bool lt = Q[lo + half] < h;
-        lo = lt ? lo + half + 1 : lo; len = lt ? len - half - 1 : half;
+      // lower_bound of h in Q: bucket directory, then three branch-free probes (buckets hold ~1 hash)
+      const uint32_t bkt = l2e_bucket(h, a.shiftA);
+      int lo = tab[bkt];
+      const int cnt = (int)tab[bkt + 1] - lo;
+      const uint32_t q0 = Q[lo], q1 = Q[lo + 1], q2 = Q[lo + 2];
+      bool match = (cnt > 0 && q0 == h) || (cnt > 1 && q1 == h) || (cnt > 2 && q2 == h);
+      lo += (cnt > 0 && q0 < h) + (cnt > 1 && q1 < h) + (cnt > 2 && q2 < h);
+      if (cnt > 3) {
+        int hi2 = (int)tab[bkt + 1];
+        if (lo == (int)tab[bkt] + 3) { while (lo < hi2 && Q[lo] < h) lo++; match = lo < hi2 && Q[lo] == h; }
       }
       const uint32_t j = (uint32_t)lo;
-      const bool match = ((int)j < s) && (Q[min((int)j, s - 1)] == h);
-      // rank s (hashes above every query hash) never reaches the pivot: such events are no-ops
-      const uint32_t base = j | (match ? EV_M : 0u);
-      const bool can = (int)j < s;
       const uint32_t pd = rc.z >> 16, nd = rc.z & 0xFFFFu, back = rc.w & 0xFFFFu, fwd = rc.w >> 16;
+      // rank >= s (hash above every query hash) never reaches the pivot => no-op
+      const uint32_t code = ev_rank(j) | (match ? EV_M : 0u);
+      const bool can = (int)j < s;
       // this record ENTERS the window
       uint32_t pos, wb; bool sc;
       if (r < e0) { pos = r - b0; wb = b0; sc = (r == e0 - 1); }
       else { wb = (back > r - b0) ? b0 : r - back; pos = nInit + (r - e0) + (wb - b0); sc = (r != last - 1); }
-      const bool isNew = !(pd != 0xFFFFu && r - pd >= wb);     // no earlier twin inside the window
-      ev[pos] = (uint16_t)(base | EV_D | ((can && isNew) ? EV_E : 0u) | (sc ? EV_S : 0u));
+      const bool isNew = can && !(pd != 0xFFFFu && r - pd >= wb);     // no earlier twin inside the window
+      ev[pos] = (uint16_t)((isNew ? (code | EV_D) : nop) | (sc ? EV_S : 0u));
       // this record LEAVES the window (only if that happens no later than the step in which last-1 enters)
       if (fwd != 0xFFFFu && r + fwd <= last - 1) {
         const uint32_t we = r + fwd;
-        const bool gone = !(nd != 0xFFFFu && r + nd < we);     // no later twin still inside the window
+        const bool gone = can && !(nd != 0xFFFFu && r + nd < we);     // no later twin still inside the window
         const uint32_t posr = nInit + (r - b0) + (we - e0);
-        ev[posr] = (uint16_t)(base | ((can && gone) ? EV_E : 0u) | ((rc.y >> 31) ? 0u : EV_S));
+        ev[posr] = (uint16_t)((gone ? code : nop) | ((rc.y >> 31) ? 0u : EV_S));
       }
     }
   }
@@ -428,7 +458,6 @@ static constexpr int L2S_WARPS = 4;
 
 __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
 __device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(addr), "r"(v) : "memory"); }
-__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
 __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(addr), "r"(v) : "memory"); }
 
 __global__ void __launch_bounds__(L2S_WARPS * 32)
@@ -437,67 +466,111 @@ l2_seq_kernel(const L2PArgs a)
   extern __shared__ __align__(16) uint32_t smem[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const uint32_t gid = blockIdx.x * (L2S_WARPS * 32) + threadIdx.x;
-  // word i of this lane's state lives at warpBase + i*32 + lane: bank == lane for every access
-  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem) + ((uint32_t)wid * a.laneWords * 32u + (uint32_t)lane) * 4u;
-  const uint32_t pbase = sbase + a.gapWords * 128u;
-  for (uint32_t i = 0; i < a.laneWords; i++) sts_u32(sbase + i * 128u, 0u);
+  const uint32_t wbase = (uint32_t)__cvta_generic_to_shared(smem) + (uint32_t)wid * a.warpBytes;
+  for (uint32_t i = lane * 4u; i < a.warpBytes; i += 128u) sts_u32(wbase + i, 0u);
+  __syncwarp();
+  const uint32_t sb = wbase + (uint32_t)lane;
 
   uint32_t c = 0, nEv = 0; int s = 1;
   if (gid < a.C) { c = a.perm[gid]; nEv = a.cNEv[c]; s = a.sCount[a.cFrag[c]]; }
-  const uint4 *strm = reinterpret_cast<const uint4 *>(a.events) + (nEv ? a.cOff[c] : 0u);
-  const uint32_t nCh = (nEv + 7) >> 3;
-  uint32_t maxCh = nCh;
-  for (int o = 16; o; o >>= 1) maxCh = max(maxCh, __shfl_xor_sync(0xffffffffu, maxCh, o));
+  const uint4 *strm = reinterpret_cast<const uint4 *>(a.events) + (nEv ? (size_t)a.cOff[c] * 2 : (size_t)0);
+  const uint32_t nSt = (nEv + 15) >> 4;                                  // 32-byte steps of this lane
+  uint32_t maxSt = nSt;
+  for (int o = 16; o; o >>= 1) maxSt = max(maxSt, __shfl_xor_sync(0xffffffffu, maxSt, o));
+  const uint32_t nop = ev_rank((uint32_t)s) | EV_M | EV_D;
+  const uint32_t nop2 = nop | (nop << 16);
+  const uint4 nop4 = make_uint4(nop2, nop2, nop2, nop2);
 
-  int t = s, G = 0, P = 0, best = 0;
-  uint32_t nrem = 0, firstN = 0, lastN = 0, ovf = 0;
-  uint4 nxt = make_uint4(0, 0, 0, 0);
-  if (nCh) nxt = __ldg(strm);
-  for (uint32_t ch = 0; ch < maxCh; ch++) {
-    const uint4 cur = nxt;
-    if (ch + 1 < nCh) nxt = __ldg(strm + ch + 1);
-    const uint32_t wv[4] = {cur.x, cur.y, cur.z, cur.w};
+  // pivot rank t kept as T5 = t << 5; Z = t + (#foreign hashes below the pivot) - s + 1  (invariant Z <= 1, t maximal);
+  // P = query hashes present below the pivot
+  uint32_t T5 = (uint32_t)s << 5;
+  int Z = 1, P = 0, best = 0;
+  uint32_t firstK = 0, lastK = 0, acc = 0;
+  // each lane streams its own events: 32 bytes (one DRAM sector) per step, loaded two steps ahead
+  uint4 n1a = nop4, n1b = nop4, n2a = nop4, n2b = nop4;
+  if (nSt > 0) { n1a = __ldg(strm); n1b = __ldg(strm + 1); }
+  if (nSt > 1) { n2a = __ldg(strm + 2); n2b = __ldg(strm + 3); }
+  for (uint32_t stp = 0; stp < maxSt; stp++) {
+    const uint4 ca = n1a, cb = n1b;
+    n1a = n2a; n1b = n2b; n2a = nop4; n2b = nop4;
+    if (stp + 2 < nSt) { n2a = __ldg(strm + 2 * (stp + 2)); n2b = __ldg(strm + 2 * (stp + 2) + 1); }
+    const uint32_t wv[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+    const uint32_t kb = stp * 16;
 #pragma unroll
-    for (int q = 0; q < 8; q++) {
-      uint32_t ev = (q & 1) ? (wv[q >> 1] >> 16) : (wv[q >> 1] & 0xFFFFu);
-      const bool valid = ch * 8 + q < nEv;
-      ev = valid ? ev : 0u;
-      const uint32_t j = ev & L2_JMASK;
-      const bool ins = ev & EV_D, eff = ev & EV_E;
-      const bool m = eff && (ev & EV_M), nm = eff && !(ev & EV_M);
-      const int dir = ins ? 1 : -1;
-      const uint32_t ga = sbase + (j >> 2) * 128u + (j & 3u);
-      const uint32_t pa = pbase + (j >> 5) * 128u;
-      const uint32_t g = lds_u8(ga);
-      const uint32_t pw = lds_u32(pa);
-      ovf |= (nm && ins && g == 255u) ? 1u : 0u;
-      if (nm) sts_u8(ga, g + dir);
-      if (m) sts_u32(pa, pw ^ (1u << (j & 31u)));
-      const bool below = (int)j < t;
-      P += (m && below) ? dir : 0;
-      G += (nm && below) ? dir : 0;
-      // the pivot moves by at most one rank per event (down only after an insert, up only after a removal)
-      const bool down = t + G > s;
-      const int tt = t - (down ? 1 : 0);
-      const int gv = (int)lds_u8(sbase + ((uint32_t)tt >> 2) * 128u + ((uint32_t)tt & 3u));
-      const int pv = (int)((lds_u32(pbase + ((uint32_t)tt >> 5) * 128u) >> (tt & 31)) & 1u);
-      const bool up = !down && t < s && (t + 1 + G + gv <= s);
-      G += up ? gv : (down ? -gv : 0);
-      P += up ? pv : (down ? -pv : 0);
-      t = tt + (up ? 1 : 0);
-      nrem += (valid && !ins) ? 1u : 0u;
-      if (ev & EV_S) {
-        if (P > best) { best = P; firstN = nrem; lastN = nrem; }
-        else if (P == best) lastN = nrem;
-      }
+    for (int q = 0; q < 16; q++) {
+      const uint32_t ev = (q & 1) ? (wv[q >> 1] >> 16) : wv[q >> 1];      // the upper half of an even code is masked off below
+      const uint32_t k = kb + q;
+      // One event, written with explicit predication: the kernel is bound by the integer ALU pipe, and the
+      // compiler's select-based if-conversion costs twice the operations.  Same statement in C:
+      //   je = ev & 0xFFE0; g = state[je]; acc |= g; state[je] = g + (M ? 0x80 : dir)   (dir = insert ? +1 : -1)
+      //   if (je < T5) { if (M) P += dir; else Z += dir; }
+      //   down = Z > 1; if (down) T5 -= 32; gt = state[T5]; cnt = gt & 0x7F; pv = gt >> 7; up = Z + cnt <= 0;
+      //   if (down) { Z -= cnt + 1; P -= pv; }  if (up) { Z += cnt + 1; P += pv; T5 += 32; }
+      //   if (S && P >= best) { lastK = k; if (P > best) { best = P; firstK = k; } }
+      asm volatile(
+        "{\n\t"
+        ".reg .pred pM, pD, pS, pBM, pBN, pDn, pUp, pGE, pGT;\n\t"
+        ".reg .b32 je, aj, g, t1, dir, dl, nv, at, gt, cnt, pv, c1, zc;\n\t"
+        "and.b32 je, %7, 0xFFE0;\n\t"
+        "add.u32 aj, %8, je;\n\t"
+        "ld.shared.u8 g, [aj];\n\t"
+        "and.b32 t1, %7, 1;\n\t"  "setp.ne.u32 pM, t1, 0;\n\t"
+        "and.b32 t1, %7, 2;\n\t"  "setp.ne.u32 pD, t1, 0;\n\t"
+        "and.b32 t1, %7, 4;\n\t"  "setp.ne.u32 pS, t1, 0;\n\t"
+        "selp.s32 dir, 1, -1, pD;\n\t"
+        "selp.b32 dl, 0x80, dir, pM;\n\t"
+        "or.b32 %6, %6, g;\n\t"
+        "add.u32 nv, g, dl;\n\t"
+        "st.shared.u8 [aj], nv;\n\t"
+        "setp.lt.and.u32 pBM, je, %0, pM;\n\t"
+        "setp.lt.and.u32 pBN, je, %0, !pM;\n\t"
+        "@pBM add.s32 %2, %2, dir;\n\t"
+        "@pBN add.s32 %1, %1, dir;\n\t"
+        "setp.gt.s32 pDn, %1, 1;\n\t"
+        "@pDn sub.u32 %0, %0, 32;\n\t"
+        "add.u32 at, %8, %0;\n\t"
+        "ld.shared.u8 gt, [at];\n\t"
+        "and.b32 cnt, gt, 0x7F;\n\t"
+        "shr.u32 pv, gt, 7;\n\t"
+        "add.s32 zc, %1, cnt;\n\t"
+        "setp.le.s32 pUp, zc, 0;\n\t"
+        "add.s32 c1, cnt, 1;\n\t"
+        "@pDn sub.s32 %1, %1, c1;\n\t"
+        "@pDn sub.s32 %2, %2, pv;\n\t"
+        "@pUp add.s32 %1, %1, c1;\n\t"
+        "@pUp add.s32 %2, %2, pv;\n\t"
+        "@pUp add.u32 %0, %0, 32;\n\t"
+        "setp.ge.and.s32 pGE, %2, %3, pS;\n\t"
+        "setp.gt.and.s32 pGT, %2, %3, pS;\n\t"
+        "@pGE mov.u32 %5, %9;\n\t"
+        "@pGT mov.u32 %4, %9;\n\t"
+        "@pGT mov.s32 %3, %2;\n\t"
+        "}"
+        : "+r"(T5), "+r"(Z), "+r"(P), "+r"(best), "+r"(firstK), "+r"(lastK), "+r"(acc)
+        : "r"(ev), "r"(sb), "r"(k)
+        : "memory");
     }
   }
   if (gid < a.C && nEv) {
-    if (ovf) a.cBest[c] = -1;
+    if (acc & 0x40u) a.cBest[c] = -1;                        // a counter came near its 7-bit range: exact kernel
     else {
-      const uint32_t b0 = a.cB0[c];
-      const int first = best > 0 ? rec_wpos(a.rec, b0 + firstN) : 0;   // "first" stays 0 while best == 0 (as in the sweep above)
-      const int lastp = rec_wpos(a.rec, b0 + lastN);
+      // event index -> window start: b = b0 + #{records that left at or before that event}; the event position of
+      // the removal of record r is monotone in r (same formula as in l2_events_kernel)
+      const uint32_t b0 = a.cB0[c], e0 = a.cE0[c], last = a.cLast[c], nInit = e0 - b0;
+      const uint32_t back = __ldg(&a.rec[last - 1].w) & 0xFFFFu;
+      const uint32_t nRem = (back > last - 1 - b0) ? 0u : last - 1 - back - b0;
+      auto removed_upto = [&](uint32_t K) -> uint32_t {
+        uint32_t lo = 0, hi = nRem;                          // first r' with pos(b0 + r') > K
+        while (lo < hi) {
+          const uint32_t mid = (lo + hi) >> 1, r = b0 + mid;
+          const uint32_t fwd = __ldg(&a.rec[r].w) >> 16;
+          const uint32_t posr = nInit + mid + (r + fwd - e0);
+          if (posr <= K) lo = mid + 1; else hi = mid;
+        }
+        return lo;
+      };
+      const int first = best > 0 ? rec_wpos(a.rec, b0 + removed_upto(firstK)) : 0;   // "first" stays 0 while best == 0 (as in the sweep above)
+      const int lastp = rec_wpos(a.rec, b0 + removed_upto(lastK));
       a.cPos[c] = (first + lastp) / 2;
       a.cBest[c] = best;
     }
@@ -819,7 +892,7 @@ void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_
             BANI_CUDA(cudaMemsetAsync(d_n2.p, 0, 8, st));
             l2.scratch = scratch.p; l2.cPos = cPos.p; l2.cBest = cBest.p; l2.onlyFlagged = 1;
             {
-              Stage sg(ctx, "l2");
+              Stage sgb(ctx, "l2_bounds");
               BANI_SCRATCH(uint32_t, fragCandOff, (size_t)F + 1);
               frag_cand_off_kernel<<<nblk((uint64_t)F + 1), 256, 0, st>>>(cFrag.p, C, F, fragCandOff.p);
               ctx->launches++;
@@ -827,10 +900,10 @@ void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_
               lp.fragCandOff = fragCandOff.p; lp.fragHash = fragHash.p; lp.segStart = segStart.p; lp.sCount = sCount.p;
               lp.rec = ix->rec.p; lp.contigRecOff = ix->contigRecOff.p; lp.fragLen = fragLen; lp.cmw = cmw;
               // fast path: needs the window links of the index (cmw >= 2) and ranks that fit the event code
-              lp.sLimit = (cmw >= 2 && ix->cmw == cmw) ? std::min(smax, L2_JMASK) : 0;
-              { int lg = 0; while ((8 << (lg + 1)) <= w + 1) lg++; lp.dirShift = std::max(22 - lg, 10); }   // hashes of minimizers crowd below 2^32 * c/(w+1)
-              lp.gapWords = (uint32_t)(std::max(lp.sLimit, 1) + 1 + 3) / 4;
-              lp.laneWords = lp.gapWords + (uint32_t)(std::max(lp.sLimit, 1) >> 5) + 1;
+              lp.sLimit = (cmw >= 2 && ix->cmw == cmw) ? std::min(smax, L2_SMAX) : 0;
+              // bucket width near 0 ~ 2^32 / (s * w): minimizer hashes are minima of w hashes, density w/2^32 at 0
+              { int sh = 22; while (sh > 8 && ((uint64_t)std::max(smax, 1) * (uint64_t)w << sh) > (1ull << 32)) sh--; lp.shiftA = sh; }
+              lp.warpBytes = (uint32_t)(std::max(lp.sLimit, 1) + 1) * 32u;      // one state byte per rank 0..s and lane
               BANI_SCRATCH(uint32_t, cB0, C);          // (one scratch slot per source line)
               BANI_SCRATCH(uint32_t, cE0, C);
               BANI_SCRATCH(uint32_t, cLast, C);
@@ -848,11 +921,11 @@ void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_
                   unsigned long long totalChunks = 0;
                   BANI_CUDA(cudaMemcpyAsync(&totalChunks, cOff64.p + C, 8, cudaMemcpyDeviceToHost, st));
                   BANI_CUDA(cudaStreamSynchronize(st));
-                  if (totalChunks > 0xfffffff0ull) fail(BANI_ERR_LIMIT, "query chunk schedules more than 2^35 window events");
+                  if (totalChunks > 0xfffffff0ull) fail(BANI_ERR_LIMIT, "query chunk schedules more than 2^36 window events");
                   tb = cub_scan_u32_temp((size_t)C + 1);
                   BANI_SCRATCH(uint8_t, tmp2, tb);
                   cub_exclusive_sum_u32(tmp2.p, tb, cChunks.p, cOff.p, (size_t)C + 1, st);
-                  BANI_SCRATCH(uint16_t, events, (size_t)totalChunks * 8 + 64);
+                  BANI_SCRATCH(uint16_t, events, (size_t)totalChunks * 16 + 64);
                   lp.events = events.p; }
                 BANI_SCRATCH(uint32_t, skey, C);
                 BANI_SCRATCH(uint32_t, skey2, C);
@@ -864,8 +937,8 @@ void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_
                   cub_sort_pairs_u32(tmp.p, tb, skey.p, skey2.p, sval.p, perm.p, C, 20, st); }
                 lp.perm = perm.p;
                 static bool attrSet = false;
-                const size_t shmE = 4 * (size_t)lp.sLimit + 2 * 1026 + 16;
-                const size_t shmS = 4 * (size_t)L2S_WARPS * 32 * lp.laneWords;
+                const size_t shmE = 4 * ((size_t)lp.sLimit + 4) + 2 * (L2E_TAB + 2) + 16;
+                const size_t shmS = (size_t)L2S_WARPS * lp.warpBytes;
                 if (shmE > 200 * 1024 || shmS > 200 * 1024) fail(BANI_ERR_INTERNAL, "L2 shared-memory budget exceeded");
                 if (!attrSet) {
                   BANI_CUDA(cudaFuncSetAttribute(l2_events_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -873,10 +946,15 @@ void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_
                   BANI_CUDA(cudaFuncSetAttribute(l2_seq_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
                   attrSet = true;
                 }
-                l2_events_kernel<<<F, L2E_THREADS, shmE, st>>>(lp); ctx->launches++;
-                l2_seq_kernel<<<nblk(C, L2S_WARPS * 32), L2S_WARPS * 32, shmS, st>>>(lp); ctx->launches++;
+                sgb.stop();
+                { Stage sg(ctx, "l2_events");
+                  l2_events_kernel<<<F, L2E_THREADS, shmE, st>>>(lp); ctx->launches++; }
+                { Stage sg(ctx, "l2_seq");
+                  l2_seq_kernel<<<nblk(C, L2S_WARPS * 32), L2S_WARPS * 32, shmS, st>>>(lp); ctx->launches++; }
               }
-              // exact slow path for whatever the fast path flagged (uint8 counter overflow, very large sketches)
+              sgb.stop();
+              // exact slow path for whatever the fast path flagged (counter overflow, very large sketches)
+              Stage sgs(ctx, "l2_exact");
               l2_kernel<<<blocks, 64, 0, st>>>(l2); ctx->launches++;
             }
 
