@@ -370,85 +370,88 @@ __global__ void l2_sortkey_kernel(const uint32_t *cNEv, uint32_t C, uint32_t *ke
 }
 
 static constexpr int L2E_THREADS = 256;
-static constexpr int L2E_TAB = 2048;             // buckets: [0,1024) width 2^shiftA from 0; [1024,2048) width 2^22 over the whole range
+static constexpr int L2E_BUCKETS = 4096;         // directory over h >> shiftA (clamped): ~s*w/2^(32-shiftA) <= 1 query hash per bucket near 0
 
-__device__ __forceinline__ uint32_t l2e_bucket(uint32_t h, int shiftA)
-{
-  const uint32_t a = h >> shiftA;
-  return a < 1024u ? a : 1024u + (h >> 22);
-}
-
+// Event schedule of one candidate in closed form.  With rb = r - b0, nInit = e0 - b0, nAll = last - b0 and the
+// per-record window links of the index (back, fwd, tie; index.cu):
+//   r ENTERS at position 2*rb - mb, mb = min(back, rb)  (= rb for the records of the first window, whose mb == rb... see below)
+//            the window then starts at record r - mb; r adds a new distinct hash iff its previous twin is further than mb
+//            back; a scoring point follows iff rb + 1 >= nInit (the first window is complete) and r is not the last record
+//   r LEAVES at position 2*rb + fwd, if rb + fwd < nAll (no later than the step in which the last record enters);
+//            the window then ends before record r + fwd; r removes a distinct hash iff its next twin is at least fwd
+//            ahead; a scoring point follows unless another record enters in the same step (tie)
+// (positions: the first window's records occupy 0 .. nInit-1 because for them back >= rb, i.e. mb = rb; afterwards
+//  "enters" and "leaves" interleave by time, leaves first on ties -- the merge of computeMap.hpp:455-492.)
 __global__ void __launch_bounds__(L2E_THREADS)
 l2_events_kernel(const L2PArgs a)
 {
   extern __shared__ __align__(16) uint32_t smem[];
+  __shared__ uint32_t s_wsum[L2E_THREADS / 32];
   const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const uint32_t c0 = a.fragCandOff[f], c1 = a.fragCandOff[f + 1];
   if (c0 == c1) return;
   const int s = a.sCount[f];
   if (s < 1 || s > a.sLimit) return;
-  uint32_t *Q = smem;                                          // sLimit + 3 words (3 probes past the end read the pad)
-  uint16_t *tab = (uint16_t *)(smem + a.sLimit + 4);           // L2E_TAB + 1 entries
+  uint32_t *Q = smem;                                          // s hashes + 3 sentinels
+  uint32_t *tab = smem + a.sLimit + 4;                         // L2E_BUCKETS + 1: bucket -> first rank
   {
     const uint32_t *Qg = a.fragHash + a.segStart[f];
     for (int i = tid; i < s + 3; i += L2E_THREADS) Q[i] = i < s ? Qg[i] : 0xFFFFFFFFu;
+    for (int i = tid; i <= L2E_BUCKETS; i += L2E_THREADS) tab[i] = 0;
     __syncthreads();
-    const uint32_t split = a.shiftA + 10 >= 32 ? 0xFFFFFFFFu : (1024u << a.shiftA);
-    for (int bkt = tid; bkt <= L2E_TAB; bkt += L2E_THREADS) {
-      int lo = 0, hi = s;
-      if (bkt == L2E_TAB) lo = s;
-      else {
-        // lowest hash of the bucket
-        const uint32_t v = bkt < 1024 ? ((uint32_t)bkt << a.shiftA) : max((uint32_t)(bkt - 1024) << 22, split);
-        if (bkt < 1024 && ((uint64_t)bkt << a.shiftA) > 0xFFFFFFFFull) lo = s;
-        else while (lo < hi) { int mid = (lo + hi) >> 1; if (Q[mid] < v) lo = mid + 1; else hi = mid; }
-      }
-      tab[bkt] = (uint16_t)lo;
-    }
+    for (int i = tid; i < s; i += L2E_THREADS) atomicAdd(&tab[min(Q[i] >> a.shiftA, (uint32_t)(L2E_BUCKETS - 1))], 1u);
+    __syncthreads();
+    // exclusive prefix over the bucket counts: 16 consecutive buckets per thread
+    constexpr int PER = L2E_BUCKETS / L2E_THREADS;
+    uint32_t cnt[PER], sum = 0;
+#pragma unroll
+    for (int i = 0; i < PER; i++) { cnt[i] = tab[tid * PER + i]; sum += cnt[i]; }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) s_wsum[wid] = incl;
+    __syncthreads();
+    uint32_t run = incl - sum;
+    for (int i = 0; i < wid; i++) run += s_wsum[i];
+#pragma unroll
+    for (int i = 0; i < PER; i++) { tab[tid * PER + i] = run; run += cnt[i]; }
+    if (tid == L2E_THREADS - 1) tab[L2E_BUCKETS] = run;
     __syncthreads();
   }
   const uint32_t nop = ev_rank((uint32_t)s) | EV_M | EV_D;
   for (uint32_t c = c0 + wid; c < c1; c += L2E_THREADS / 32) {
     const uint32_t nEv = a.cNEv[c];
     if (nEv == 0) continue;
-    const uint32_t b0 = a.cB0[c], e0 = a.cE0[c], last = a.cLast[c], nInit = e0 - b0;
+    const uint32_t b0 = a.cB0[c], nInit = a.cE0[c] - b0, nAll = a.cLast[c] - b0;
     uint16_t *ev = a.events + (size_t)a.cOff[c] * 16;
     if (lane < ((16u - (nEv & 15u)) & 15u)) ev[nEv + lane] = (uint16_t)nop;    // pad the last 32-byte step
-    uint32_t r = b0 + lane;
+    const uint4 *rp = a.rec + b0;
+    uint32_t rb = lane;
     uint4 nxt = make_uint4(0, 0, 0, 0);
-    if (r < last) nxt = __ldg(&a.rec[r]);
-    for (; r < last; r += 32) {
+    if (rb < nAll) nxt = __ldg(rp + rb);
+    for (; rb < nAll; rb += 32) {
       const uint4 rc = nxt;
-      if (r + 32 < last) nxt = __ldg(&a.rec[r + 32]);
+      if (rb + 32 < nAll) nxt = __ldg(rp + rb + 32);
       const uint32_t h = rc.x;
-      // lower_bound of h in Q: bucket directory, then three branch-free probes (buckets hold ~1 hash)
-      const uint32_t bkt = l2e_bucket(h, a.shiftA);
-      int lo = tab[bkt];
-      const int cnt = (int)tab[bkt + 1] - lo;
-      const uint32_t q0 = Q[lo], q1 = Q[lo + 1], q2 = Q[lo + 2];
-      bool match = (cnt > 0 && q0 == h) || (cnt > 1 && q1 == h) || (cnt > 2 && q2 == h);
-      lo += (cnt > 0 && q0 < h) + (cnt > 1 && q1 < h) + (cnt > 2 && q2 < h);
-      if (cnt > 3) {
-        int hi2 = (int)tab[bkt + 1];
-        if (lo == (int)tab[bkt] + 3) { while (lo < hi2 && Q[lo] < h) lo++; match = lo < hi2 && Q[lo] == h; }
-      }
-      const uint32_t j = (uint32_t)lo;
-      const uint32_t pd = rc.z >> 16, nd = rc.z & 0xFFFFu, back = rc.w & 0xFFFFu, fwd = rc.w >> 16;
-      // rank >= s (hash above every query hash) never reaches the pivot => no-op
+      // rank of h in Q: directory, then two probes (the sentinels and the sorted order make them unconditional)
+      uint32_t j = tab[min(h >> a.shiftA, (uint32_t)(L2E_BUCKETS - 1))];
+      const uint32_t q0 = Q[j], q1 = Q[j + 1];
+      bool match = (q0 == h) || (q1 == h);
+      j += (q0 < h) + (q1 < h);
+      if (q1 < h) { while (Q[j] < h) j++; match = Q[j] == h; }              // crowded bucket (rare)
+      const bool can = (int)j < s;                                          // rank s: above every query hash => no-op
       const uint32_t code = ev_rank(j) | (match ? EV_M : 0u);
-      const bool can = (int)j < s;
-      // this record ENTERS the window
-      uint32_t pos, wb; bool sc;
-      if (r < e0) { pos = r - b0; wb = b0; sc = (r == e0 - 1); }
-      else { wb = (back > r - b0) ? b0 : r - back; pos = nInit + (r - e0) + (wb - b0); sc = (r != last - 1); }
-      const bool isNew = can && !(pd != 0xFFFFu && r - pd >= wb);     // no earlier twin inside the window
-      ev[pos] = (uint16_t)((isNew ? (code | EV_D) : nop) | (sc ? EV_S : 0u));
-      // this record LEAVES the window (only if that happens no later than the step in which last-1 enters)
-      if (fwd != 0xFFFFu && r + fwd <= last - 1) {
-        const uint32_t we = r + fwd;
-        const bool gone = can && !(nd != 0xFFFFu && r + nd < we);     // no later twin still inside the window
-        const uint32_t posr = nInit + (r - b0) + (we - e0);
-        ev[posr] = (uint16_t)((gone ? code : nop) | ((rc.y >> 31) ? 0u : EV_S));
+      const uint32_t pd = rc.z >> 16, nd = rc.z & 0xFFFFu, back = rc.w & 0xFFFFu, fwd = rc.w >> 16;
+      const uint32_t rb2 = rb * 2;
+      // r ENTERS
+      const uint32_t mb = min(back, rb);
+      const bool isNew = can && pd > mb;
+      const bool sc = (rb + 1 >= nInit) && (rb + 1 != nAll);
+      ev[rb2 - mb] = (uint16_t)((isNew ? (code | EV_D) : nop) | (sc ? EV_S : 0u));
+      // r LEAVES
+      if (rb + fwd < nAll) {
+        const bool gone = can && nd >= fwd;
+        ev[rb2 + fwd] = (uint16_t)((gone ? code : nop) | ((rc.y >> 31) ? 0u : EV_S));
       }
     }
   }
@@ -902,7 +905,7 @@ void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_
               // fast path: needs the window links of the index (cmw >= 2) and ranks that fit the event code
               lp.sLimit = (cmw >= 2 && ix->cmw == cmw) ? std::min(smax, L2_SMAX) : 0;
               // bucket width near 0 ~ 2^32 / (s * w): minimizer hashes are minima of w hashes, density w/2^32 at 0
-              { int sh = 22; while (sh > 8 && ((uint64_t)std::max(smax, 1) * (uint64_t)w << sh) > (1ull << 32)) sh--; lp.shiftA = sh; }
+              { int sh = 20; while (sh > 8 && ((uint64_t)std::max(smax, 1) * (uint64_t)w << sh) > (1ull << 32)) sh--; lp.shiftA = sh; }
               lp.warpBytes = (uint32_t)(std::max(lp.sLimit, 1) + 1) * 32u;      // one state byte per rank 0..s and lane
               BANI_SCRATCH(uint32_t, cB0, C);          // (one scratch slot per source line)
               BANI_SCRATCH(uint32_t, cE0, C);
@@ -937,7 +940,7 @@ void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_
                   cub_sort_pairs_u32(tmp.p, tb, skey.p, skey2.p, sval.p, perm.p, C, 20, st); }
                 lp.perm = perm.p;
                 static bool attrSet = false;
-                const size_t shmE = 4 * ((size_t)lp.sLimit + 4) + 2 * (L2E_TAB + 2) + 16;
+                const size_t shmE = 4 * ((size_t)lp.sLimit + 4) + 4 * (L2E_BUCKETS + 4);
                 const size_t shmS = (size_t)L2S_WARPS * lp.warpBytes;
                 if (shmE > 200 * 1024 || shmS > 200 * 1024) fail(BANI_ERR_INTERNAL, "L2 shared-memory budget exceeded");
                 if (!attrSet) {
