@@ -303,18 +303,38 @@ def main_ours(a):
         pass
     peak, peak_src = (peaks.get("hbm_gbs"), "measured (MEASURED_PEAKS.json)") if peaks.get("hbm_gbs") else (6650.0, "fallback (B200_PROFILING.md)")
     st = last["stats"]
-    algo = {k: v[1] / max(a.steps, 1) for k, v in prof.items()}
-    algo["l2"] = 12.0 * ctr["n2"]                                  # position-ordered records scanned, 12 B each
-    algo["ref_sketch"] = st["total_len"] / 4.0 + 12.0 * st["n_minimizers"]
     stages = {k: {"ms": v[0] / max(a.steps, 1), "launches": v[2] // max(a.steps, 1),
-                  "algo_GB": algo.get(k, 0) / 1e9} for k, v in prof.items()}
-    dom = max(stages, key=lambda k: stages[k]["ms"]) if stages else None
+                  "algo_GB": v[1] / max(a.steps, 1) / 1e9} for k, v in prof.items()}
+    # stage timers -> kernels (the two sketch stages run the same kernel); algorithmic bytes per stage are set
+    # next to the launches in csrc/ (DESIGN.md section 4 lists the formulas)
+    KERNEL_OF = {"ref_sketch": "sketch_kernel", "q_sketch": "sketch_kernel", "l2_events": "l2_events_kernel",
+                 "l2_seq": "l2_seq_kernel", "frag_l1": "frag_l1_kernel", "lookup": "lookup_kernel",
+                 "q_sort_unique": "sort_unique_kernel", "l2_bounds": "l2_bounds_kernel"}
+    kernels = {}
+    for k, v in stages.items():
+        kk = kernels.setdefault(KERNEL_OF.get(k, k), {"ms": 0.0, "launches": 0, "algo_GB": 0.0})
+        kk["ms"] += v["ms"]; kk["launches"] += v["launches"]; kk["algo_GB"] += v["algo_GB"]
+    dom = max(kernels, key=lambda k: kernels[k]["ms"]) if kernels else None
     roof = None
     if dom:
-        ach = stages[dom]["algo_GB"] / (stages[dom]["ms"] / 1e3) if stages[dom]["ms"] > 0 else 0.0
+        kd = kernels[dom]
+        ach = kd["algo_GB"] / (kd["ms"] / 1e3) if kd["ms"] > 0 else 0.0
+        traffic, traffic_src = None, None
+        try:        # DRAM bytes per algorithmic byte of this kernel, from the committed ncu --set full capture
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_dram_traffic.json")))
+            if dom in tj["kernels"]:
+                traffic = tj["kernels"][dom]["dram_bytes_per_algorithmic_byte"] * kd["algo_GB"] * 1e9 / max(kd["launches"], 1)
+                traffic_src = tj["kernels"][dom]["source"]
+        except Exception:
+            pass
         roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": stages[dom]["algo_GB"] * 1e9 / max(stages[dom]["launches"], 1)}
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "launches_per_step": kd["launches"], "avg_launch_ms": kd["ms"] / max(kd["launches"], 1),
+                "algorithmic_bytes_per_launch": kd["algo_GB"] * 1e9 / max(kd["launches"], 1),
+                "share_of_step": kd["ms"] / (sec_res * 1e3),
+                "note": "integer hash/compare kernels: the limiter is the INT32 ALU / L1TEX pipe, not HBM (DESIGN.md section 6)"}
+    kern_tab = {k: {"ms": round(v["ms"], 3), "launches": v["launches"], "GBps": round(v["algo_GB"] / (v["ms"] / 1e3), 1) if v["ms"] > 0 else 0.0}
+                for k, v in sorted(kernels.items(), key=lambda kv: -kv[1]["ms"])}
 
     line = {
         "metric": METRIC, "value": pairs / sec_res, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
@@ -331,6 +351,7 @@ def main_ours(a):
                 "h2d_bytes_per_step": int(nG * L), "d2h_bytes_per_step": int(last["d2h"])},
         "gpu_launches": int(launches),
         "roofline": roof,
+        "kernels": kern_tab,
         "stages": stages,
     }
     if world == 1 and not a.no_cpu_baseline:

@@ -177,6 +177,8 @@ struct Stage {
     idx = c->profEvents.size(); c->profEvents.push_back(e);
   }
   void bytes(double b) { if (idx != (size_t)-1) c->profEvents[idx].bytes = b; }
+  size_t id() const { return idx; }                       // to set the bytes after the stage has been closed
+  static void set_bytes(Ctx *c, size_t id, double b) { if (id != (size_t)-1 && id < c->profEvents.size()) c->profEvents[id].bytes = b; }
   void stop() { if (idx != (size_t)-1) { cudaEventRecord(c->profEvents[idx].b, c->stream); idx = (size_t)-1; } }
   ~Stage() { stop(); }
 };

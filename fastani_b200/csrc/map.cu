@@ -761,6 +761,7 @@ void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_
         fragHash = ctx->view<uint32_t>(__LINE__, std::max<uint64_t>(cap, 1));
         Stage sg(ctx, "q_sketch", (double)F * fragLen / 4.0);
         T = sketch_sequences(ctx, d_desc.p, F, flen.data(), fragHash.p, nullptr, nullptr, cap, segStart.p);
+        sg.bytes((double)F * fragLen / 4.0 + 4.0 * (double)T);
         if (T <= cap) break;
         cap = T;
       }
@@ -813,7 +814,7 @@ void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_
           static const long long maxFast = [] { const char *e = getenv("BANI_FRAG_L1_MAX"); long long v = e ? atoll(e) : (long long)FRAG_L1_MAX;
                                                 return std::max(0ll, std::min(v, (long long)FRAG_L1_MAX)); }();
           uint32_t hClass[8];
-          { Stage sg(ctx, "frag_l1", 12.0 * N);
+          { Stage sg(ctx, "frag_l1", 12.0 * N);                // 4 B list entry + 8 B (seqId, wpos) per hit
             frag_classify(ctx, segStart.p, hitOff.p, F, candCount.p, fragClass.p, classCount.p, classList.p, (unsigned long long)maxFast);
             BANI_CUDA(cudaMemcpyAsync(hClass, classCount.p, sizeof hClass, cudaMemcpyDeviceToHost, st));
             BANI_CUDA(cudaStreamSynchronize(st));
@@ -894,8 +895,10 @@ void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_
             BANI_SCRATCH(unsigned long long, d_n2, 1);
             BANI_CUDA(cudaMemsetAsync(d_n2.p, 0, 8, st));
             l2.scratch = scratch.p; l2.cPos = cPos.p; l2.cBest = cBest.p; l2.onlyFlagged = 1;
+            size_t idEv = (size_t)-1; double evBytes = 0;
             {
-              Stage sgb(ctx, "l2_bounds");
+              unsigned long long totalSteps = 0;
+              Stage sgb(ctx, "l2_bounds", 12.0 * C);
               BANI_SCRATCH(uint32_t, fragCandOff, (size_t)F + 1);
               frag_cand_off_kernel<<<nblk((uint64_t)F + 1), 256, 0, st>>>(cFrag.p, C, F, fragCandOff.p);
               ctx->launches++;
@@ -924,6 +927,7 @@ void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_
                   unsigned long long totalChunks = 0;
                   BANI_CUDA(cudaMemcpyAsync(&totalChunks, cOff64.p + C, 8, cudaMemcpyDeviceToHost, st));
                   BANI_CUDA(cudaStreamSynchronize(st));
+                  totalSteps = totalChunks;
                   if (totalChunks > 0xfffffff0ull) fail(BANI_ERR_LIMIT, "query chunk schedules more than 2^36 window events");
                   tb = cub_scan_u32_temp((size_t)C + 1);
                   BANI_SCRATCH(uint8_t, tmp2, tb);
@@ -950,9 +954,9 @@ void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_
                   attrSet = true;
                 }
                 sgb.stop();
-                { Stage sg(ctx, "l2_events");
+                { Stage sg(ctx, "l2_events"); idEv = sg.id(); evBytes = 32.0 * (double)totalSteps;
                   l2_events_kernel<<<F, L2E_THREADS, shmE, st>>>(lp); ctx->launches++; }
-                { Stage sg(ctx, "l2_seq");
+                { Stage sg(ctx, "l2_seq", evBytes + 16.0 * C);       // the event codes in, {position, shared} out
                   l2_seq_kernel<<<nblk(C, L2S_WARPS * 32), L2S_WARPS * 32, shmS, st>>>(lp); ctx->launches++; }
               }
               sgb.stop();
@@ -977,6 +981,7 @@ void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_
             BANI_CUDA(cudaMemcpyAsync(&n2, d_n2.p, 8, cudaMemcpyDeviceToHost, st));
             BANI_CUDA(cudaStreamSynchronize(st));
             out.ctr.n2 += n2; out.ctr.mappings += R;
+            Stage::set_bytes(ctx, idEv, 16.0 * (double)n2 + evBytes);   // 16-byte records in, 2-byte event codes out
             if (R > 0) {
               BANI_SCRATCH(bani_mapping, rows, R);
               DevBuf<int32_t> rFrag(R, st);
