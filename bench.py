@@ -42,7 +42,8 @@ def parse_args():
     ap.add_argument("--strains", type=int, default=20)
     ap.add_argument("--genome-len", type=int, default=5_000_000)
     ap.add_argument("--seed", type=int, default=3)
-    ap.add_argument("--ref-sample", type=int, default=50, help="reference arm: miniature is S x S genomes")
+    ap.add_argument("--ref-sample-refs", type=int, default=0, help="reference arm: references in the bounded sample (0 = one per host core)")
+    ap.add_argument("--ref-sample-queries", type=int, default=4, help="reference arm: queries in the bounded sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -118,23 +119,27 @@ def write_fasta(path, name, seq):
         f.write(body)
 
 
-def miniature(a, gen):
-    """S x S miniature with the full workload's related-pair fraction (1/clusters): queries = strain 1 and
-    references = strain 0 of S clusters, so each query has exactly one related reference out of S."""
-    S = min(a.ref_sample, a.clusters)
-    refs = [(c, 0) for c in range(S)]
-    qrys = [(c, 1) for c in range(S)]
-    return S, qrys, refs
+def miniature(a, cores):
+    """Bounded sample of the workload for the CPU arm.  The reference parallelises over REFERENCES only (one OpenMP
+    thread per reference shard, core_genome_identity.cpp:55), so the sample has as many references as the box has
+    cores (all threads busy, as in the full 1000-reference run) and a few queries, and keeps the full run's related
+    fraction: reference i = strain 2*(i // clusters) of cluster i % clusters, query q = strain 1 of cluster q, so
+    query q is related to the references i = q (mod clusters): ~R/clusters of R, i.e. 1 in `clusters`, like 20 of 1000."""
+    R = max(1, min(a.ref_sample_refs or cores, a.clusters * ((a.strains + 1) // 2)))
+    Q = max(1, min(a.ref_sample_queries, a.clusters))
+    refs = [(i % a.clusters, 2 * (i // a.clusters)) for i in range(R)]
+    qrys = [(q, 1) for q in range(Q)]
+    return qrys, refs
 
 
 def run_reference_cli(a, gen, steps, warmup):
-    """Times oracle/_ref/fastANI_ref (the unmodified reference, OpenMP) on the miniature; returns
+    """Times oracle/_ref/fastANI_ref (the unmodified reference, OpenMP) on the bounded sample; returns
     (pairs_per_s, seconds_per_step, cores, sample description)."""
     cli = os.path.join(ROOT, "oracle", "_ref", "fastANI_ref")
     if not os.path.exists(cli):
         raise RuntimeError("oracle/_ref/fastANI_ref is missing (build it with `make -C oracle` where /root/reference exists)")
     cores = os.cpu_count() or 1
-    S, qrys, refs = miniature(a, gen)
+    qrys, refs = miniature(a, cores)
     tmp = tempfile.mkdtemp(prefix="bani_ref_")
     try:
         ql, rl = os.path.join(tmp, "q.txt"), os.path.join(tmp, "r.txt")
@@ -159,10 +164,11 @@ def run_reference_cli(a, gen, steps, warmup):
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
     sec = float(np.mean(times))
-    sample = ("%dx%d miniature of the workload (queries = strain 1, references = strain 0 of %d clusters: one related "
-              "reference per query = the full run's 1/%d related fraction), %.1f Mbp genomes, fastANI_ref -t %d, %d output rows"
-              % (S, S, S, a.clusters, a.genome_len / 1e6, cores, rows))
-    return S * S / sec, sec, cores, sample
+    nrel = sum(1 for (qc, _) in qrys for (rc, _) in refs if rc == qc)
+    sample = ("%d queries x %d references of the workload (%d related pairs of %d; full run: 1 in %d), "
+              "%.1f Mbp genomes, fastANI_ref -t %d (one thread per reference), %d output rows, FASTA on local disk"
+              % (len(qrys), len(refs), nrel, len(qrys) * len(refs), a.clusters, a.genome_len / 1e6, cores, rows))
+    return len(qrys) * len(refs) / sec, sec, cores, sample
 
 
 def numpy_gen(a):

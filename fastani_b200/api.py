@@ -102,7 +102,7 @@ def load_library():
 
 
 EXPORTED_SYMBOLS = [
-    "bani_last_error", "bani_version", "bani_params_default", "bani_recommended_window_size",
+    "bani_last_error", "bani_version", "bani_params_default", "bani_recommended_window_size", "bani_device_count",
     "bani_stat_min_hits_relaxed", "bani_stat_identity", "bani_ctx_create", "bani_ctx_destroy", "bani_ctx_params",
     "bani_ctx_sync", "bani_ctx_stream", "bani_ctx_launch_count", "bani_ctx_profile_enable", "bani_ctx_profile_read", "bani_host_alloc", "bani_host_free", "bani_genome_create",
     "bani_genome_create_batch", "bani_genome_destroy", "bani_genome_info", "bani_genome_decode", "bani_index_build",

@@ -20,6 +20,8 @@ def _deps_mtime():
         for f in files:
             m = max(m, os.path.getmtime(os.path.join(root, f)))
     m = max(m, os.path.getmtime(os.path.join(HERE, "..", "include", "fastani_b200.h")))
+    for f in os.listdir(os.path.join(HERE, "host")):
+        m = max(m, os.path.getmtime(os.path.join(HERE, "host", f)))
     return m
 
 
@@ -51,7 +53,22 @@ def build(force=False, verbose=False):
                         "-o", LIB] + objs + ["-cudart", "static"], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    build_cli()
     return LIB
+
+
+def build_cli():
+    """The fastANI command line (C++ host above the C ABI): fastani_b200/bin/fastANI."""
+    bindir = os.path.join(HERE, "bin")
+    os.makedirs(bindir, exist_ok=True)
+    exe = os.path.join(bindir, "fastANI")
+    src = os.path.join(HERE, "host", "fastani_main.cpp")
+    cmd = ["g++", "-O2", "-std=c++17", "-Wall", src, "-o", exe, "-L" + OUT, "-lfastani_b200", "-lz", "-lpthread",
+           "-Wl,-rpath,$ORIGIN/../lib"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("CLI build failed:\n%s\n%s" % (r.stdout, r.stderr))
+    return exe
 
 
 if __name__ == "__main__":

@@ -57,6 +57,17 @@ int bani_stat_identity(int shared, int s, int k, float *identity, float *upper)
   BANI_CATCH
 }
 
+int bani_device_count(int32_t *n)
+{
+  BANI_TRY
+  if (!n) fail(BANI_ERR_ARG, "null argument");
+  int c = 0;
+  if (cudaGetDeviceCount(&c) != cudaSuccess) { (void)cudaGetLastError(); c = 0; }
+  *n = c;
+  return BANI_OK;
+  BANI_CATCH
+}
+
 int bani_ctx_create(int device, const bani_params *p, bani_ctx **out)
 {
   BANI_TRY

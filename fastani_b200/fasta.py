@@ -5,7 +5,7 @@ import gzip
 
 def read_fasta(path):
     """Returns [(name, sequence_bytes)] in file order.  The name is the header up to the first
-    whitespace; sequence lines are concatenated (whitespace removed) until a line that starts
+    whitespace; sequence lines are concatenated (bytes kept as they are, like kseq) until a line that starts
     with '>', '@' or '+'; after '+', quality lines are skipped until they cover the sequence
     length; CRLF tolerated."""
     with open(path, "rb") as fh:
@@ -27,7 +27,7 @@ def read_fasta(path):
             s = lines[i].rstrip(b"\r")
             if s[:1] in (b">", b"@", b"+"):
                 break
-            chunks.append(s.translate(None, b" \t"))
+            chunks.append(s)
             i += 1
         seq = b"".join(chunks)
         if i < n and lines[i][:1] == b"+":

@@ -1,0 +1,241 @@
+// fastani_main.cpp -- the fastANI command line on top of libfastani_b200.so.
+//
+// Same options and output files as the reference CLI (src/map/include/parseCmdArgs.hpp:118-256,
+// src/cgi/core_genome_identity.cpp:27-167): -q/--query, --ql/--queryList, -r/--ref, --rl/--refList, -o/--output,
+// -k/--kmer, --fragLen, --minFraction, --maxRatioDiff, --visualize, --matrix, -t/--threads, -s/--sanityCheck,
+// -v/--version, -h/--help.  Differences, all on the host side:
+//   * the reference list is split over GPUs (--gpus N, default: every visible device), not over OpenMP threads;
+//     -t sets the host threads of the ingest stage.  Results do not depend on the split.
+//   * every genome file is read ONCE (parallel inflate + parse), its length for the --minFraction filter comes from
+//     the same pass (the reference reads each file again in computeGenomeLengths, computeCoreIdentity.hpp:48-92)
+//   * without --visualize the per-pair reduction runs on the device (bani_map_cgi); with it, the mapping rows come
+//     back and cgi::computeCGI runs on the host because the .visual file needs the surviving rows themselves
+#include <atomic>
+#include <chrono>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <sstream>
+#include <thread>
+#include "ani_host.hpp"
+
+using namespace skch;
+typedef std::chrono::high_resolution_clock Clock;
+
+static void usage(const char *prog, std::ostream &o)
+{
+  o << "-----------------\n"
+       "fastANI (B200-native engine): alignment-free whole-genome Average Nucleotide Identity (ANI)\n"
+       "-----------------\n"
+       "Example usage:\n"
+       "$ " << prog << " -q genome1.fa -r genome2.fa -o output.txt\n"
+       "$ " << prog << " -q genome1.fa --rl genome_list.txt -o output.txt\n\n"
+       "OPTIONS\n"
+       "     -h, --help            print this help page\n"
+       "     -r, --ref <value>     reference genome (fasta/fastq)[.gz]\n"
+       "     --rl, --refList <value>   a file containing list of reference genome files, one genome per line\n"
+       "     -q, --query <value>   query genome (fasta/fastq)[.gz]\n"
+       "     --ql, --queryList <value> a file containing list of query genome files, one genome per line\n"
+       "     -k, --kmer <value>    kmer size <= 32 [default : 16]\n"
+       "     -t, --threads <value> host threads for reading the genome files [default : 1]\n"
+       "     --gpus <value>        GPUs to split the reference list over [default : all visible]\n"
+       "     --fragLen <value>     fragment length [default : 3,000]\n"
+       "     --minFraction <value> minimum fraction of genome that must be shared for trusting ANI [default : 0.2]\n"
+       "     --maxRatioDiff <value> maximum difference between (Total Ref. Length/Total Occ. Hashes) and\n"
+       "                           (Total Ref. Length/Total No. Hashes) [default : 100.0]\n"
+       "     --visualize           output mappings for visualization (<output>.visual)\n"
+       "     --matrix              also output ANI values as lower triangular matrix (<output>.matrix)\n"
+       "     -o, --output <value>  output file name\n"
+       "     -s, --sanityCheck     run sanity check\n"
+       "     -v, --version         show version\n";
+}
+
+static std::string trim(const std::string &s)
+{
+  size_t a = 0, b = s.size();
+  while (a < b && isspace((unsigned char)s[a])) a++;
+  while (b > a && isspace((unsigned char)s[b - 1])) b--;
+  return s.substr(a, b - a);
+}
+
+static void parseFileList(const std::string &fileToRead, std::vector<std::string> &fileList)   // parseCmdArgs.hpp:34-52
+{
+  std::ifstream in(fileToRead);
+  if (in.fail()) { std::cerr << "ERROR, skch::parseFileList, Could not open " << fileToRead << "\n"; exit(1); }
+  std::string line;
+  while (std::getline(in, line)) { line = trim(line); if (!line.empty()) fileList.push_back(line); }
+}
+
+static void validateInputFiles(const std::vector<std::string> &q, const std::vector<std::string> &r)   // parseCmdArgs.hpp:59-90
+{
+  if (q.empty() || r.empty()) { std::cerr << "ERROR, skch::validateInputFiles, Count of query and ref genomes should be non-zero" << std::endl; exit(1); }
+  for (const auto *lst : {&q, &r})
+    for (const auto &e : *lst) { std::ifstream in(e); if (in.fail()) { std::cerr << "ERROR, skch::validateInputFiles, Could not open " << e << std::endl; exit(1); } }
+}
+
+static void parseandSave(int argc, char **argv, Parameters &p)
+{
+  std::string refName, refList, qryName, qryList;
+  bool help = false, version = false;
+  auto need = [&](int &i) -> const char * { if (i + 1 >= argc) { usage(argv[0], std::cout); exit(1); } return argv[++i]; };
+  for (int i = 1; i < argc; i++) {
+    const std::string a = argv[i];
+    if (a == "-h" || a == "--help") help = true;
+    else if (a == "-r" || a == "--ref") refName = need(i);
+    else if (a == "--rl" || a == "--refList") refList = need(i);
+    else if (a == "-q" || a == "--query") qryName = need(i);
+    else if (a == "--ql" || a == "--queryList") qryList = need(i);
+    else if (a == "-k" || a == "--kmer") p.kmerSize = atoi(need(i));
+    else if (a == "-t" || a == "--threads") p.threads = atoi(need(i));
+    else if (a == "--gpus") p.gpus = atoi(need(i));
+    else if (a == "--fragLen") p.minReadLength = atoi(need(i));
+    else if (a == "--minFraction") p.minFraction = (float)atof(need(i));
+    else if (a == "--maxRatioDiff") p.maxRatioDiff = (float)atof(need(i));
+    else if (a == "--visualize") p.visualize = true;
+    else if (a == "--matrix") p.matrixOutput = true;
+    else if (a == "-o" || a == "--output") p.outFileName = need(i);
+    else if (a == "-s" || a == "--sanityCheck") p.sanityCheck = true;
+    else if (a == "-v" || a == "--version") version = true;
+    else { usage(argv[0], std::cout); exit(1); }
+  }
+  if (help) { usage(argv[0], std::cout); exit(0); }
+  if (version) { std::cerr << "version 1.33 (" << bani_version() << ")\n\n"; exit(0); }
+  if (refName.empty() && refList.empty()) { std::cerr << "Provide reference file (s)\n"; exit(1); }
+  if (qryName.empty() && qryList.empty()) { std::cerr << "Provide query file (s)\n"; exit(1); }
+  if (!refName.empty()) p.refSequences.push_back(refName); else parseFileList(refList, p.refSequences);
+  if (!qryName.empty()) p.querySequences.push_back(qryName); else parseFileList(qryList, p.querySequences);
+  if (!(p.minFraction >= 0.0f && p.minFraction <= 1.0f)) { std::cerr << "ERROR, --minFraction must lie in [0, 1]\n"; exit(1); }
+  if (p.threads < 1) p.threads = 1;
+  bani_params c = p.c();
+  const int w = bani_recommended_window_size(&c);          // Stat::recommendedWindowSize, parseCmdArgs.hpp:244-247
+  if (w < 0) { std::cerr << "ERROR, " << bani_last_error() << "\n"; exit(1); }
+  p.windowSize = w;
+  std::cerr << ">>>>>>>>>>>>>>>>>>\nReference = [" ;
+  for (size_t i = 0; i < p.refSequences.size(); i++) std::cerr << (i ? ", " : "") << p.refSequences[i];
+  std::cerr << "]\nQuery = [";
+  for (size_t i = 0; i < p.querySequences.size(); i++) std::cerr << (i ? ", " : "") << p.querySequences[i];
+  std::cerr << "]\nKmer size = " << p.kmerSize << "\nFragment length = " << p.minReadLength << "\nThreads = " << p.threads
+            << "\nANI output file = " << p.outFileName << "\nSanity Check  = " << p.sanityCheck << "\n>>>>>>>>>>>>>>>>>>" << std::endl;
+  validateInputFiles(p.querySequences, p.refSequences);
+}
+
+int main(int argc, char **argv)
+{
+  if (argc == 3 && std::string(argv[1]) == "--dumpContigs") {       // test hook for the reader: name, length, crc32 per contig
+    try {
+      const bani_host::HostGenome g = bani_host::read_genome(argv[2]);
+      for (const auto &c : g.contigs)
+        std::cout << c.name << "\t" << c.len << "\t" << crc32(0L, g.seq.data() + c.off, (uInt)c.len) << "\n";
+      return 0;
+    } catch (const std::exception &e) { std::cerr << "ERROR, " << e.what() << std::endl; return 1; }
+  }
+  Parameters parameters;
+  parseandSave(argc, argv, parameters);
+  const std::string fileName = parameters.outFileName;
+  try {
+    // ---- ingest: every distinct file once, in parallel
+    auto t0 = Clock::now();
+    std::unordered_map<std::string, int> pathId; std::vector<std::string> paths;
+    for (const auto *lst : {&parameters.querySequences, &parameters.refSequences})
+      for (const auto &e : *lst) if (!pathId.count(e)) { pathId[e] = (int)paths.size(); paths.push_back(e); }
+    std::vector<bani_host::HostGenome> genomes(paths.size());
+    {
+      std::atomic<size_t> next(0); std::mutex emu; std::string err;
+      auto work = [&]() {
+        for (size_t i; (i = next++) < paths.size();) {
+          try { genomes[i] = bani_host::read_genome(paths[i]); }
+          catch (const std::exception &e) { std::lock_guard<std::mutex> l(emu); err = e.what(); }
+        }
+      };
+      std::vector<std::thread> th;
+      for (int i = 0; i < std::min<int>(parameters.threads, (int)paths.size()); i++) th.emplace_back(work);
+      for (auto &t : th) t.join();
+      if (!err.empty()) throw std::runtime_error(err);
+    }
+    std::unordered_map<std::string, uint64_t> genomeLengths;
+    for (size_t i = 0; i < paths.size(); i++) genomeLengths[paths[i]] = cgi::genomeLength(genomes[i], parameters.minReadLength);
+    std::cerr << "INFO, skch::main, Time spent reading " << paths.size() << " genome files : "
+              << std::chrono::duration<double>(Clock::now() - t0).count() << " sec" << std::endl;
+
+    // ---- one reference shard per GPU
+    int32_t nDev = 0;
+    if (bani_device_count(&nDev) != BANI_OK || nDev == 0) throw std::runtime_error("no CUDA device available (this program has no CPU path)");
+    const int G = parameters.gpus > 0 ? std::min(parameters.gpus, nDev) : nDev;
+    const auto shards = cgi::splitReferenceGenomes((int)parameters.refSequences.size(), G);
+    std::vector<cgi::CGI_Results> finalResults;
+    std::vector<std::string> visual(G);
+    std::vector<char> sanity(G, 1); std::vector<float> ratioDiffs(G, 1.0f);
+    std::mutex mu; std::string err;
+
+    auto shardWork = [&](int g) {
+      try {
+        auto t1 = Clock::now();
+        bani_params cp = parameters.c();
+        bani_ctx *ctx = nullptr;
+        check(bani_ctx_create(g, &cp, &ctx), "bani_ctx_create");
+        {
+          // genomes this device needs: its reference shard and every query, each file once
+          std::vector<int> need; std::unordered_map<int, int> slot;
+          auto want = [&](const std::string &path) { const int id = pathId.at(path); if (!slot.count(id)) { slot[id] = (int)need.size(); need.push_back(id); } return slot[id]; };
+          std::vector<int> refSlot, qrySlot;
+          for (int j : shards[g]) refSlot.push_back(want(parameters.refSequences[j]));
+          for (const auto &q : parameters.querySequences) qrySlot.push_back(want(q));
+          std::vector<const bani_host::HostGenome *> hs; for (int id : need) hs.push_back(&genomes[id]);
+          std::vector<std::unique_ptr<DeviceGenome>> dev;
+          upload_genomes(ctx, hs, dev);
+          std::vector<const DeviceGenome *> refs; std::vector<std::string> shardRefNames;
+          for (size_t i = 0; i < refSlot.size(); i++) { refs.push_back(dev[refSlot[i]].get()); shardRefNames.push_back(parameters.refSequences[shards[g][i]]); }
+
+          Sketch referSketch(ctx, parameters, refs);                      // HP1
+          if (g == 0) std::cerr << "INFO [GPU 0], skch::main, Time spent sketching the reference : "
+                                << std::chrono::duration<double>(Clock::now() - t1).count() << " sec" << std::endl;
+          std::vector<cgi::CGI_Results> local;
+          sanity[g] = referSketch.sanityCheck(parameters.maxRatioDiff); ratioDiffs[g] = referSketch.getRatioDifference();
+          if (sanity[g]) {
+            t1 = Clock::now();
+            if (parameters.visualize) {
+              std::ostringstream vis;
+              for (size_t q = 0; q < qrySlot.size(); q++) {
+                MappingResultsVector_t mapResults; uint64_t totalQueryFragments = 0;
+                Map mapper(ctx, parameters, referSketch, *dev[qrySlot[q]], totalQueryFragments,
+                           std::bind(Map::insertL2ResultsToVec, std::ref(mapResults), std::placeholders::_1));     // HP2
+                cgi::computeCGI(parameters, mapResults, mapper, referSketch, totalQueryFragments, q, parameters.querySequences[q],
+                                shardRefNames, &vis, local);
+              }
+              visual[g] = vis.str();
+            } else {
+              std::vector<bani_genome *> qh; for (int s : qrySlot) qh.push_back(dev[s]->h);
+              bani_cgi_result *res = nullptr; uint64_t n = 0; std::vector<uint64_t> tot(qh.size()); bani_map_counters ctr;
+              check(bani_map_cgi(ctx, referSketch.handle(), qh.data(), (int32_t)qh.size(), &res, &n, tot.data(), &ctr), "bani_map_cgi");   // HP2 + reduction
+              for (uint64_t i = 0; i < n; i++)
+                local.push_back(cgi::CGI_Results{res[i].refGenomeId, res[i].qryGenomeId, res[i].countSeq, res[i].totalQueryFragments, res[i].identity});
+              bani_free(res);
+            }
+            if (g == 0) std::cerr << "INFO [GPU 0], skch::main, Time spent mapping " << qrySlot.size() << " query genome(s) : "
+                                  << std::chrono::duration<double>(Clock::now() - t1).count() << " sec" << std::endl;
+          }
+          cgi::correctRefGenomeIds(local, g, G);
+          std::lock_guard<std::mutex> l(mu);
+          finalResults.insert(finalResults.end(), local.begin(), local.end());
+        }
+        bani_ctx_destroy(ctx);
+      } catch (const std::exception &e) { std::lock_guard<std::mutex> l(mu); err = e.what(); }
+    };
+    {
+      std::vector<std::thread> th;
+      for (int g = 0; g < G; g++) th.emplace_back(shardWork, g);
+      for (auto &t : th) t.join();
+    }
+    if (!err.empty()) throw std::runtime_error(err);
+    for (int g = 0; g < G; g++)
+      if (!sanity[g]) std::cerr << "ERROR :: SPLIT " << g << "'s ratio difference " << ratioDiffs[g] << " exceeds maximum thresholds." << std::endl;
+
+    cgi::outputCGI(parameters, genomeLengths, finalResults, fileName);
+    if (parameters.matrixOutput) cgi::outputPhylip(parameters, genomeLengths, finalResults, fileName);
+    if (parameters.visualize) { std::ofstream o(fileName + ".visual"); for (int g = 0; g < G; g++) o << visual[g]; }
+  } catch (const std::exception &e) {
+    std::cerr << "ERROR, " << e.what() << std::endl;
+    return 1;
+  }
+  return 0;
+}

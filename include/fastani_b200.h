@@ -102,6 +102,10 @@ BANI_API int bani_recommended_window_size(const bani_params *p);
 BANI_API int bani_stat_min_hits_relaxed(int s, int k, float perc_identity);
 BANI_API int bani_stat_identity(int shared, int s, int k, float *identity, float *upper_bound);
 
+/* Number of usable CUDA devices (0 without a driver / GPU); lets a host program shard the reference list
+ * (cgi::splitReferenceGenomes, computeCoreIdentity.hpp:457-474) without linking the CUDA runtime itself. */
+BANI_API int bani_device_count(int32_t *n);
+
 /* ---- context -------------------------------------------------------------- */
 BANI_API int  bani_ctx_create(int device, const bani_params *p, bani_ctx **out);
 BANI_API void bani_ctx_destroy(bani_ctx *ctx);

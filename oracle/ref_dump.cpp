@@ -55,7 +55,7 @@ static void fill_params(skch::Parameters &p, int k, int fragLen)
 
 int main(int argc, char **argv)
 {
-  if (argc < 2) { fprintf(stderr, "usage: ref_dump hash|wsize|stats|sketch|map ...\n"); return 2; }
+  if (argc < 2) { fprintf(stderr, "usage: ref_dump hash|wsize|stats|contigs|sketch|map ...\n"); return 2; }
   std::string mode = argv[1];
 
   if (mode == "hash" && argc == 3) {
@@ -79,6 +79,18 @@ int main(int argc, char **argv)
       uint32_t a, b; memcpy(&a, &nucIdentity, 4); memcpy(&b, &nucIdentityUpperBound, 4);
       printf("%d %u %u\n", x, a, b);
     }
+    return 0;
+  }
+  if (mode == "contigs" && argc == 3) {
+    /* what the reference's own reader (kseq_read, src/common/kseq.h) yields for a file: name, length, crc32 */
+    gzFile fp = gzopen(argv[2], "r");
+    if (!fp) { fprintf(stderr, "cannot open %s\n", argv[2]); return 1; }
+    kseq_t *seq = kseq_init(fp);
+    int len;
+    while ((len = kseq_read(seq)) >= 0)
+      printf("%s\t%d\t%lu\n", seq->name.s, len, (unsigned long)crc32(0L, (const Bytef *)seq->seq.s, (uInt)seq->seq.l));
+    kseq_destroy(seq);
+    gzclose(fp);
     return 0;
   }
   if (mode == "sketch" && argc >= 6) {

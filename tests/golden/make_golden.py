@@ -12,6 +12,8 @@ Fixtures:
   s2e.k16.map                   all 4138 MappingResult records of Shigella -> E. coli (44 B each)
   e2s.txt / s2e.txt             fastANI_ref output lines (the reference's own goldens)
   *.fna.gz                      the two real genomes of the reference's tests/data (gzip -9)
+  tricky.fq + tricky.contigs.txt  a hand-made FASTA/FASTQ mix and what the reference's kseq_read yields for it
+                                (name, length, crc32 per record; `ref_dump contigs`)
 """
 import hashlib
 import json

@@ -253,3 +253,68 @@ def test_hit_paths_agree():
         assert r.returncode == 0, r.stderr[-2000:]
         outs.append(r.stdout)
     assert outs[0] == outs[1] == outs[2] == outs[3] and outs[0].count("\n") == 2
+
+
+def _cli_run(args, cwd):
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "fastani_b200", "bin", "fastANI")
+    r = subprocess.run([exe] + args, cwd=cwd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return r
+
+
+def test_cli_reproduces_the_reference_goldens(tmp_path):
+    """The C++ command line (fastani_b200/bin/fastANI) on the reference's own offline golden
+    (tests/fastani_tests.cpp:50-72: .txt, .matrix, .visual byte for byte) and README.md:80."""
+    os.mkdir(tmp_path / "data")
+    for n in ("Escherichia_coli_str_K12_MG1655.fna", "Shigella_flexneri_2a_01.fna"):
+        os.symlink(os.path.join(GOLDEN, n + ".gz"), tmp_path / "data" / n)          # gzopen reads both, so does the CLI
+    E, S = "data/Escherichia_coli_str_K12_MG1655.fna", "data/Shigella_flexneri_2a_01.fna"
+    for tag, q, r in (("e2s", E, S), ("s2e", S, E)):
+        _cli_run(["-q", q, "-r", r, "-o", tag + ".txt", "--matrix", "--visualize", "--gpus", "1"], tmp_path)
+        for ext in ("", ".matrix", ".visual"):
+            got = open(tmp_path / (tag + ".txt" + ext)).read()
+            assert got == open(os.path.join(GOLDEN, tag + ".txt" + ext)).read(), tag + ext
+        # without --visualize the per-pair reduction runs on the device: same .txt
+        _cli_run(["-q", q, "-r", r, "-o", tag + "_dev.txt", "--gpus", "1"], tmp_path)
+        assert open(tmp_path / (tag + "_dev.txt")).read() == open(os.path.join(GOLDEN, tag + ".txt")).read()
+    # sanity check on a pure repeat: no output rows (tests/fastani_tests.cpp:302-416)
+    rep = tmp_path / "rep.fa"
+    rep.write_bytes(b">rep\n" + b"AT" * 20000 + b"\n")
+    _cli_run(["-q", "rep.fa", "-r", "rep.fa", "-o", "rep.txt", "-s", "--maxRatioDiff", "10", "--gpus", "1"], tmp_path)
+    assert open(tmp_path / "rep.txt").read() == ""
+
+
+def test_cli_many_to_many_lists_match_the_python_host(tmp_path):
+    genomes = _cluster_set(2, 3, 60000)
+    paths = []
+    for i, g in enumerate(genomes):
+        p = tmp_path / ("g%d.fa" % i)
+        with open(p, "wb") as f:
+            for name, seq in g:
+                f.write(b">" + name.encode() + b"\n")
+                for o in range(0, len(seq), 70):
+                    f.write(seq[o:o + 70] + b"\n")
+        paths.append(str(p))
+    open(tmp_path / "ql.txt", "w").write("\n".join(paths[:4]) + "\n\n")
+    open(tmp_path / "rl.txt", "w").write("  " + "\n".join(paths[1:]) + "\n")
+    _cli_run(["--ql", "ql.txt", "--rl", "rl.txt", "-o", "out.txt", "--matrix", "-t", "3", "--gpus", "1", "--minFraction", "0.1"], tmp_path)
+    # the same through the Python host
+    from fastani_b200 import report
+    ctx = fb.Context(fb.Parameters())
+    hs = ctx.genomes(genomes)
+    q, r = list(range(4)), list(range(1, len(genomes)))
+    sk = fb.Sketch(ctx, [hs[i] for i in r])
+    res, tot, _ = fb.compute_cgi(ctx, sk, [hs[i] for i in q])
+    lens = [report.genome_length([len(s) for _, s in g], 3000) for g in genomes]
+    rows = [(int(x["qryGenomeId"]), int(x["refGenomeId"]), int(x["countSeq"]), int(x["totalQueryFragments"]), x["identity"]) for x in res]
+    want = report.output_lines(rows, [paths[i] for i in q], [paths[i] for i in r], [lens[i] for i in q], [lens[i] for i in r], 3000, 0.1)
+    got = open(tmp_path / "out.txt").read().splitlines()
+    assert sorted(got) == sorted(want) and len(got) >= 6
+    assert [g.split("\t")[0] for g in got] == sorted(g.split("\t")[0] for g in got)      # grouped by query, in list order
+    m = open(tmp_path / "out.txt.matrix").read().splitlines()
+    assert m[0] == str(len(genomes)) and m[1] == paths[0] and len(m) == 1 + len(genomes)
+    # host CGI path (--visualize) gives the same table
+    _cli_run(["--ql", "ql.txt", "--rl", "rl.txt", "-o", "vis.txt", "--visualize", "--gpus", "1", "--minFraction", "0.1"], tmp_path)
+    assert open(tmp_path / "vis.txt").read() == open(tmp_path / "out.txt").read()

@@ -81,7 +81,7 @@ def test_argument_errors():
 def test_fasta_reader(tmp_path):
     p = tmp_path / "x.fa"
     p.write_bytes(b">c1 desc\r\nACGT\r\nacgtn\r\n\r\n>c2\nTT TT\n@fq1\nACGTAC\n+\nIIIIII\n@fq2 x\nGG\n+\n@I\n")
-    assert fb.read_fasta(str(p)) == [("c1", b"ACGTacgtn"), ("c2", b"TTTT"), ("fq1", b"ACGTAC"), ("fq2", b"GG")]
+    assert fb.read_fasta(str(p)) == [("c1", b"ACGTacgtn"), ("c2", b"TT TT"), ("fq1", b"ACGTAC"), ("fq2", b"GG")]     # kseq keeps inner blanks
     import gzip
     gz = tmp_path / "x.fa.gz"
     gz.write_bytes(gzip.compress(p.read_bytes()))
@@ -117,3 +117,41 @@ def test_output_filter_and_format():
     out = report.output_lines(rows, ["q0", "q1"], ["r0", "r1"], [150000, 150000], [150000, 90000], 3000, 0.2)
     assert out == ["q0\tr0\t97.7507\t10\t100", "q1\tr0\t80\t20\t50"]
     assert report.genome_length([2999, 3000, 7000], 3000) == 9000
+
+
+def _cli():
+    from fastani_b200 import build
+    exe = os.path.join(ROOT, "fastani_b200", "bin", "fastANI")
+    if not os.path.exists(exe):
+        build.build_cli()
+    return exe
+
+
+def test_readers_have_kseq_semantics(tmp_path):
+    """The C++ ingest (host/kseq_reader.hpp) and the Python reader against what the reference's own kseq_read yields
+    (tests/golden/tricky.contigs.txt = `ref_dump contigs tricky.fq`): garbage before the first header, comments, CRLF,
+    empty lines, FASTQ records, inner blanks, a FASTQ record whose quality spans two lines, no trailing newline."""
+    import subprocess, zlib, gzip
+    tricky = os.path.join(GOLDEN, "tricky.fq")
+    want = [ln.split("\t") for ln in open(os.path.join(GOLDEN, "tricky.contigs.txt")).read().splitlines()]
+    gz = tmp_path / "tricky.fq.gz"
+    gz.write_bytes(gzip.compress(open(tricky, "rb").read()))
+    for f in (tricky, str(gz)):
+        r = subprocess.run([_cli(), "--dumpContigs", f], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert [ln.split("\t") for ln in r.stdout.splitlines()] == want
+        assert [[n, str(len(s)), str(zlib.crc32(s) & 0xFFFFFFFF)] for n, s in fb.read_fasta(f)] == want
+    for f in (os.path.join(GOLDEN, "edge_mixed.fa"), os.path.join(GOLDEN, "Shigella_flexneri_2a_01.fna.gz")):
+        r = subprocess.run([_cli(), "--dumpContigs", f], capture_output=True, text=True)
+        assert [ln.split("\t") for ln in r.stdout.splitlines()] == [[n, str(len(s)), str(zlib.crc32(s) & 0xFFFFFFFF)] for n, s in fb.read_fasta(f)]
+
+
+def test_cli_fails_loudly_without_gpu(tmp_path):
+    import subprocess
+    if _has_gpu():
+        pytest.skip("GPU present")
+    f = os.path.join(GOLDEN, "edge_mixed.fa")
+    r = subprocess.run([_cli(), "-q", f, "-r", f, "-o", str(tmp_path / "o.txt")], capture_output=True, text=True)
+    assert r.returncode == 1 and "no CUDA device" in r.stderr
+    r = subprocess.run([_cli(), "-q", f], capture_output=True, text=True)
+    assert r.returncode == 1 and "Provide reference file" in r.stderr
