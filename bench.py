@@ -220,14 +220,20 @@ def main_ours(a):
     ctx = fb.Context(fb.Parameters(), device=local)
     nG = a.clusters * a.strains
     L = a.genome_len
-    # ---- synthetic genomes into ONE pinned host buffer (what a FASTA reader would fill)
-    host = ctx.pinned(nG * L)
-    for g in range(nG):
-        c, s = divmod(g, a.strains)
-        ctx.synth_genome(a.seed, c + 1, s, 6000 * s, L, out=host[g * L:(g + 1) * L])
-    off = np.arange(nG + 1, dtype=np.int64) * L
-    gen_off = np.arange(nG + 1, dtype=np.int32)
+    # ---- work split (N > 1): rank r owns the references r, r+N, ... (splitReferenceGenomes) AND sketches the queries
+    #      r, r+N, ...; the query sketches are exchanged over NCCL, every rank maps all of them against its own shard.
+    #      With Q = R the two sets coincide, so every genome is uploaded to exactly one GPU.
     my_refs = parallel.shard_refs(nG, world, rank)
+    my_qrys = list(range(rank, nG, world))
+    need = sorted(set(my_refs) | set(my_qrys))
+    slot = {g: i for i, g in enumerate(need)}
+    # ---- synthetic genomes into ONE pinned host buffer (what a FASTA reader would fill)
+    host = ctx.pinned(len(need) * L)
+    for i, g in enumerate(need):
+        c, s = divmod(g, a.strains)
+        ctx.synth_genome(a.seed, c + 1, s, 6000 * s, L, out=host[i * L:(i + 1) * L])
+    off = np.arange(len(need) + 1, dtype=np.int64) * L
+    gen_off = np.arange(len(need) + 1, dtype=np.int32)
 
     stream = torch.cuda.ExternalStream(ctx.stream, device=device)
 
@@ -244,11 +250,20 @@ def main_ours(a):
         own = genomes is None
         if own:
             genomes = ctx.genomes_from_buffer(host, off, gen_off)
-        sk = fb.Sketch(ctx, [genomes[i] for i in my_refs])
-        res, tot, ctr = fb.compute_cgi(ctx, sk, genomes)
+        sk = fb.Sketch(ctx, [genomes[slot[i]] for i in my_refs])
+        if world == 1:
+            res, tot, ctr = fb.compute_cgi(ctx, sk, genomes)
+            d2h = res.nbytes + tot.nbytes
+        else:
+            mine = fb.QuerySketch(ctx, [genomes[slot[i]] for i in my_qrys], my_qrys)
+            sketches = parallel.exchange_query_sketches(ctx, mine, world, rank, dist, device)
+            res, ctr = fb.compute_cgi_sketched(ctx, sk, sketches)
+            d2h = res.nbytes
+            for q in sketches:
+                q.close()
         cnt, idn = parallel.dense_tables(res, nG, len(my_refs))
         gc, gi = parallel.gather_tables(cnt, idn, nG, world, rank, dist=dist, device=device)
-        last.update(cnt=gc, idn=gi, ctr=ctr.as_dict(), stats=sk.stats(), d2h=res.nbytes + tot.nbytes)
+        last.update(cnt=gc, idn=gi, ctr=ctr.as_dict(), stats=sk.stats(), d2h=d2h)
         sk.close()
         if own:
             for g in genomes:
@@ -291,6 +306,10 @@ def main_ours(a):
     clocks = sampler.stop() if rank == 0 else {}
 
     pairs = float(nG) * float(nG)
+    h2d = torch.tensor([float(len(need) * L)], dtype=torch.float64, device=device)        # bytes this rank uploads per e2e step
+    if dist is not None:
+        dist.all_reduce(h2d)
+    h2d_total = float(h2d.item())
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -347,14 +366,14 @@ def main_ours(a):
         "ms_per_step": sec_res * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic",
         "config": {"workload": workload_name(a), "k": 16, "frag_len": 3000, "window": ctx.windowSize,
-                   "queries": nG, "references": nG, "parallelism": "reference list sharded round-robin over %d GPU(s)" % world,
+                   "queries": nG, "references": nG, "parallelism": ("reference list sharded round-robin over %d GPU(s)" % world) + ("; each rank sketches 1/%d of the queries, sketches all-gathered over NCCL" % world if world > 1 else ""),
                    "l2_flush": "inputs (%.1f GB packed genomes + %.1f GB index per rank) exceed the 126 MB L2" % (
                        nG * L / 4e9, 16.0 * st["n_minimizers"] / 1e9),
                    "result_check": "self pairs > 99.9%% and >= %d populated pairs: %s (min self identity %.4f)" % (nG, diag_ok, float(np.diag(idn).min())),
                    "counters_rank0": ctr},
         "clocks": clocks,
         "e2e": {"value": pairs / sec_e2e, "unit": UNIT, "ms_per_step": sec_e2e * 1e3,
-                "h2d_bytes_per_step": int(nG * L), "d2h_bytes_per_step": int(last["d2h"])},
+                "h2d_bytes_per_step": int(h2d_total), "d2h_bytes_per_step": int(last["d2h"])},
         "gpu_launches": int(launches),
         "roofline": roof,
         "kernels": kern_tab,

@@ -5,5 +5,6 @@ include/fastani_b200.h; this package is its Python host side.  There is no CPU f
 importing works anywhere, but every compute call raises if the library or a GPU is missing.
 """
 from .api import (Parameters, Context, Genome, Sketch, Map, MapCounters, BaniError,  # noqa: F401
-                  MAPPING_DTYPE, MINIMIZER_DTYPE, CGI_DTYPE, compute_cgi, load_library, library_path)
+                  MAPPING_DTYPE, MINIMIZER_DTYPE, CGI_DTYPE, compute_cgi, compute_cgi_sketched, QuerySketch,
+                  load_library, library_path)
 from .fasta import read_fasta  # noqa: F401

@@ -90,6 +90,13 @@ def load_library():
         "bani_index_lookup": (C.c_int, [vp, vp, u32, vp, vp, u64, P(u64)]),
         "bani_map_genome": (C.c_int, [vp, vp, vp, P(vp), P(u64), P(u64), P(MapCounters)]),
         "bani_map_cgi": (C.c_int, [vp, vp, P(vp), i32, P(vp), P(u64), vp, P(MapCounters)]),
+        "bani_device_count": (C.c_int, [P(i32)]),
+        "bani_qsketch_create": (C.c_int, [vp, P(vp), i32, vp, P(vp)]),
+        "bani_qsketch_destroy": (None, [vp]),
+        "bani_qsketch_info": (C.c_int, [vp, P(i32), P(u64), P(u64), P(u64)]),
+        "bani_qsketch_export": (C.c_int, [vp, vp, vp, u64]),
+        "bani_qsketch_import": (C.c_int, [vp, vp, u64, P(vp)]),
+        "bani_map_cgi_sketch": (C.c_int, [vp, vp, P(vp), i32, P(vp), P(u64), P(MapCounters)]),
         "bani_free": (None, [vp]),
         "bani_synth_genome": (C.c_int, [vp, u64, u32, u32, u32, i64, vp]),
     }
@@ -107,7 +114,8 @@ EXPORTED_SYMBOLS = [
     "bani_ctx_sync", "bani_ctx_stream", "bani_ctx_launch_count", "bani_ctx_profile_enable", "bani_ctx_profile_read", "bani_host_alloc", "bani_host_free", "bani_genome_create",
     "bani_genome_create_batch", "bani_genome_destroy", "bani_genome_info", "bani_genome_decode", "bani_index_build",
     "bani_index_destroy", "bani_index_stats", "bani_index_minimizers", "bani_index_lookup", "bani_map_genome",
-    "bani_map_cgi", "bani_free", "bani_synth_genome"]
+    "bani_map_cgi", "bani_free", "bani_synth_genome", "bani_qsketch_create", "bani_qsketch_destroy", "bani_qsketch_info",
+    "bani_qsketch_export", "bani_qsketch_import", "bani_map_cgi_sketch"]
 
 
 def _check(rc):
@@ -372,3 +380,65 @@ def compute_cgi(ctx, refSketch, query_genomes):
     else:
         out = np.empty(0, CGI_DTYPE)
     return out, tot[:len(qs)], ctr
+
+
+class QuerySketch:
+    """The first half of skch::Map as an object (Map::doL1Mapping, computeMap.hpp:252-276): sorted unique
+    minimizer hashes of every fragment of a list of query genomes, resident on the GPU.  It can be packed into
+    a flat device buffer (export_to) and rebuilt on another GPU (from_device_buffer), which is what a multi-GPU
+    run exchanges instead of sketching every query on every rank."""
+
+    def __init__(self, ctx, query_genomes=None, query_ids=None, _handle=None):
+        self.ctx = ctx
+        if _handle is not None:
+            self.h = _handle
+            return
+        qs = list(query_genomes)
+        arr = (C.c_void_p * max(len(qs), 1))(*[g.h for g in qs])
+        ids = None
+        if query_ids is not None:
+            ids = np.ascontiguousarray(query_ids, dtype=np.int32)
+            assert len(ids) == len(qs)
+        h = C.c_void_p()
+        _check(ctx.lib.bani_qsketch_create(ctx.h, arr, len(qs), ids.ctypes.data if ids is not None else None, C.byref(h)))
+        self.h = h
+
+    @classmethod
+    def from_device_buffer(cls, ctx, device_ptr, nbytes):
+        h = C.c_void_p()
+        _check(ctx.lib.bani_qsketch_import(ctx.h, C.c_void_p(int(device_ptr)), int(nbytes), C.byref(h)))
+        return cls(ctx, _handle=h)
+
+    def info(self):
+        n = C.c_int32(); f = C.c_uint64(); t = C.c_uint64(); b = C.c_uint64()
+        _check(self.ctx.lib.bani_qsketch_info(self.h, C.byref(n), C.byref(f), C.byref(t), C.byref(b)))
+        return {"n_queries": n.value, "n_fragments": f.value, "n_hashes": t.value, "export_bytes": b.value}
+
+    def export_to(self, device_ptr, cap):
+        _check(self.ctx.lib.bani_qsketch_export(self.ctx.h, self.h, C.c_void_p(int(device_ptr)), int(cap)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.bani_qsketch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def compute_cgi_sketched(ctx, refSketch, query_sketches):
+    """compute_cgi for prebuilt QuerySketch objects; qryGenomeId = the query_ids the sketches were built with."""
+    qs = list(query_sketches)
+    arr = (C.c_void_p * max(len(qs), 1))(*[q.h for q in qs])
+    res = C.c_void_p(); n = C.c_uint64(); ctr = MapCounters()
+    _check(ctx.lib.bani_map_cgi_sketch(ctx.h, refSketch.h, arr, len(qs), C.byref(res), C.byref(n), C.byref(ctr)))
+    if n.value:
+        buf = (C.c_uint8 * (CGI_DTYPE.itemsize * n.value)).from_address(res.value)
+        out = np.frombuffer(buf, dtype=CGI_DTYPE).copy()
+        ctx.lib.bani_free(res)
+    else:
+        out = np.empty(0, CGI_DTYPE)
+    return out, ctr

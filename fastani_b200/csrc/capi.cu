@@ -6,6 +6,7 @@
 struct bani_ctx    { bani::Ctx c; };
 struct bani_genome { bani::Genome g; };
 struct bani_index  { bani::Index *ix; };
+struct bani_qsketch { bani::QSketch *qs; };
 
 namespace bani {
 static thread_local std::string g_err;
@@ -352,6 +353,78 @@ int bani_map_cgi(bani_ctx *ctx, const bani_index *ix, bani_genome *const *querie
     memcpy(*results, mo.cgi.data(), sizeof(bani_cgi_result) * mo.cgi.size());
   }
   if (total_query_fragments) for (int i = 0; i < n_queries; i++) total_query_fragments[i] = mo.totalQueryFragments[i];
+  if (counters) *counters = mo.ctr;
+  return BANI_OK;
+  BANI_CATCH
+}
+
+int bani_qsketch_create(bani_ctx *ctx, bani_genome *const *queries, int32_t n_queries, const int32_t *query_ids, bani_qsketch **out)
+{
+  BANI_TRY
+  if (!ctx || n_queries < 0 || (n_queries && !queries) || !out) fail(BANI_ERR_ARG, "null argument");
+  BANI_CUDA(cudaSetDevice(ctx->c.device));
+  std::vector<const Genome *> qs(n_queries);
+  for (int i = 0; i < n_queries; i++) { if (!queries[i]) fail(BANI_ERR_ARG, "null genome handle"); qs[i] = &queries[i]->g; }
+  std::unique_ptr<bani_qsketch> h(new bani_qsketch());
+  h->qs = qsketch_create(&ctx->c, qs.data(), n_queries, query_ids);
+  *out = h.release();
+  return BANI_OK;
+  BANI_CATCH
+}
+
+void bani_qsketch_destroy(bani_qsketch *qs) { if (qs) { delete qs->qs; delete qs; } }
+
+int bani_qsketch_info(const bani_qsketch *qs, int32_t *n_queries, uint64_t *n_fragments, uint64_t *n_hashes, uint64_t *export_bytes)
+{
+  BANI_TRY
+  if (!qs || !qs->qs) fail(BANI_ERR_ARG, "null argument");
+  if (n_queries) *n_queries = (int32_t)qs->qs->queryId.size();
+  if (n_fragments) *n_fragments = qs->qs->F;
+  if (n_hashes) *n_hashes = qs->qs->T;
+  if (export_bytes) *export_bytes = qsketch_export_bytes(qs->qs);
+  return BANI_OK;
+  BANI_CATCH
+}
+
+int bani_qsketch_export(bani_ctx *ctx, const bani_qsketch *qs, void *device_buf, uint64_t cap)
+{
+  BANI_TRY
+  if (!ctx || !qs || !qs->qs || !device_buf) fail(BANI_ERR_ARG, "null argument");
+  BANI_CUDA(cudaSetDevice(ctx->c.device));
+  qsketch_export(&ctx->c, qs->qs, device_buf, cap);
+  return BANI_OK;
+  BANI_CATCH
+}
+
+int bani_qsketch_import(bani_ctx *ctx, const void *device_buf, uint64_t bytes, bani_qsketch **out)
+{
+  BANI_TRY
+  if (!ctx || !device_buf || !out) fail(BANI_ERR_ARG, "null argument");
+  BANI_CUDA(cudaSetDevice(ctx->c.device));
+  std::unique_ptr<bani_qsketch> h(new bani_qsketch());
+  h->qs = qsketch_import(&ctx->c, device_buf, bytes);
+  *out = h.release();
+  return BANI_OK;
+  BANI_CATCH
+}
+
+int bani_map_cgi_sketch(bani_ctx *ctx, const bani_index *ix, const bani_qsketch *const *sketches, int32_t n_sketches,
+                        bani_cgi_result **results, uint64_t *n_results, bani_map_counters *counters)
+{
+  BANI_TRY
+  if (!ctx || !ix || !ix->ix || n_sketches < 0 || (n_sketches && !sketches) || !results || !n_results) fail(BANI_ERR_ARG, "null argument");
+  BANI_CUDA(cudaSetDevice(ctx->c.device));
+  std::vector<const QSketch *> qs(n_sketches);
+  for (int i = 0; i < n_sketches; i++) { if (!sketches[i] || !sketches[i]->qs) fail(BANI_ERR_ARG, "null query sketch"); qs[i] = sketches[i]->qs; }
+  MapOutput mo;
+  qsketch_map(&ctx->c, ix->ix, qs.data(), n_sketches, false, true, mo);
+  *n_results = mo.cgi.size();
+  *results = nullptr;
+  if (!mo.cgi.empty()) {
+    *results = (bani_cgi_result *)malloc(sizeof(bani_cgi_result) * mo.cgi.size());
+    if (!*results) fail(BANI_ERR_NOMEM, "host allocation failed");
+    memcpy(*results, mo.cgi.data(), sizeof(bani_cgi_result) * mo.cgi.size());
+  }
   if (counters) *counters = mo.ctr;
   return BANI_OK;
   BANI_CATCH

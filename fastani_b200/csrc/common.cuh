@@ -102,6 +102,27 @@ struct Genome {
 
 struct Ctx;
 
+// ---------------------------------------------------------------- query sketch (first half of HP2)
+// Map::doL1Mapping, computeMap.hpp:252-276: per fragment the sorted unique minimizer hashes Q, s = |Q|.
+// A piece holds at most 2^17 fragments of whole query genomes; arrays are packed back to back so that a
+// sketch can be exported to one flat device buffer and moved between GPUs.
+struct QPiece {
+  int q0 = 0, nq = 0;                // local query range [q0, q0 + nq) of the owning sketch
+  int32_t F = 0; uint64_t T = 0; int smax = 0;
+  DevBuf<uint32_t> fragHash;         // T  : sorted unique hashes of fragment f at [segStart[f], segStart[f+1])
+  DevBuf<uint32_t> segStart;         // F+1
+  DevBuf<int32_t>  sCount;           // F  : s
+  DevBuf<int32_t>  fragQuery;        // F  : query slot inside the piece (0 .. nq)
+  DevBuf<int32_t>  fragSeqId;        // F  : querySeqId of the mapping records (fragment ordinal inside its genome)
+};
+struct QSketch {
+  int device = 0; int k = 0, w = 0, fragLen = 0;
+  std::vector<int32_t> queryId;          // id reported as qryGenomeId
+  std::vector<uint64_t> totalFragments;  // Map's totalQueryFragments per query
+  std::vector<std::unique_ptr<QPiece>> pieces;
+  uint64_t F = 0, T = 0;
+};
+
 // ---------------------------------------------------------------- index (HP1 output)
 struct Index {
   int device = 0;
@@ -192,7 +213,7 @@ void genome_decode(Ctx *ctx, const Genome *g, int32_t contig, uint8_t *out, int6
 // sketch.cu : windowed minimizers of a list of sequences, records compacted in
 // (sequence, wpos) order.  Outputs may be null (skipped).  Returns total records
 // (which may exceed `cap`; only the first cap are stored).
-uint64_t sketch_sequences(Ctx *ctx, const SeqDesc *d_desc, int32_t nSeq, const int32_t *h_len,
+uint64_t sketch_sequences(Ctx *ctx, const SeqDesc *d_desc, int32_t nSeq, const int32_t *h_len, int32_t uniformLen,
                           uint32_t *o_hash, int32_t *o_wpos, int32_t *o_seqId, uint64_t cap,
                           uint32_t *o_segStart /* nSeq+1 */);
 
@@ -207,6 +228,12 @@ struct MapOutput {
   bani_map_counters ctr{};
 };
 void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_t nq,
+                 bool wantRows, bool wantCgi, MapOutput &out);
+QSketch *qsketch_create(Ctx *ctx, const Genome *const *queries, int32_t nq, const int32_t *queryIds);
+uint64_t qsketch_export_bytes(const QSketch *qs);
+void qsketch_export(Ctx *ctx, const QSketch *qs, void *devBuf, uint64_t cap);
+QSketch *qsketch_import(Ctx *ctx, const void *devBuf, uint64_t bytes);
+void qsketch_map(Ctx *ctx, const Index *ix, const QSketch *const *sketches, int32_t nSketches,
                  bool wantRows, bool wantCgi, MapOutput &out);
 
 // hits.cu : per-fragment gather + shared-memory sort + L1 candidate regions

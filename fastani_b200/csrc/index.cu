@@ -191,7 +191,7 @@ Index *index_build(Ctx *ctx, Genome *const *refs, int32_t nRefs)
       if (cap > 0xfffffff0ull) fail(BANI_ERR_LIMIT, "more than 2^32 minimizers in one index shard");
       th.alloc(cap, st); tw.alloc(cap, st); ts.alloc(cap, st);
       Stage sg(ctx, "ref_sketch", (double)ix->totalLen / 4.0);
-      M = sketch_sequences(ctx, d_desc.p, nC, ix->contigLen.data(), th.p, tw.p, ts.p, cap, ix->contigRecOff.p);
+      M = sketch_sequences(ctx, d_desc.p, nC, ix->contigLen.data(), 0, th.p, tw.p, ts.p, cap, ix->contigRecOff.p);
       sg.bytes((double)ix->totalLen / 4.0 + 12.0 * (double)M);       // packed bases in, 12-byte records out
       if (M <= cap) break;
       cap = M;

@@ -618,8 +618,9 @@ struct CgiArgs {
   const int32_t *fragQuery;            // chunk-local query slot of a fragment
   const int32_t *contigGenome; const uint32_t *contigBinOff;
   int fragLen; unsigned long long totalBins; int nGenomes;
-  uint32_t *table;                     // [querySlot][totalBins] float bits, 0 = empty
-  uint8_t *touched;                    // [querySlot][nGenomes]
+  uint32_t *table;                     // [querySlot - qLo][totalBins] float bits, 0 = empty
+  uint8_t *touched;                    // [querySlot - qLo][nGenomes]
+  int qLo, qHi;                        // query slots of the piece handled by this pass
 };
 
 // 1-way: best row of each (fragment, genome) by (identity, refSeqId, refStartPos) (cgid_types.hpp:31-39,
@@ -628,17 +629,19 @@ __global__ void cgi_scatter_kernel(const CgiArgs a)
 {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.R) return;
+  const int f = a.rFrag[i];
+  const int q = a.fragQuery[f];
+  if (q < a.qLo || q >= a.qHi) return;
   const bani_mapping r = a.rows[i];
-  const int f = a.rFrag[i], g = a.contigGenome[r.refSeqId];
+  const int g = a.contigGenome[r.refSeqId];
   // rows of a fragment are contiguous and ordered by (refSeqId, refStartPos): a later row wins ties
   for (uint32_t j = i + 1; j < a.R && a.rFrag[j] == f && a.contigGenome[a.rows[j].refSeqId] == g; j++)
     if (a.rows[j].nucIdentity >= r.nucIdentity) return;
   for (uint32_t j = i; j-- > 0 && a.rFrag[j] == f && a.contigGenome[a.rows[j].refSeqId] == g;)
     if (a.rows[j].nucIdentity > r.nucIdentity) return;
-  const int q = a.fragQuery[f];
   const unsigned long long bin = a.contigBinOff[r.refSeqId] + (uint32_t)(r.refStartPos / (a.fragLen - 20));
-  atomicMax(a.table + (unsigned long long)q * a.totalBins + bin, __float_as_uint(r.nucIdentity));
-  a.touched[(size_t)q * a.nGenomes + g] = 1;
+  atomicMax(a.table + (unsigned long long)(q - a.qLo) * a.totalBins + bin, __float_as_uint(r.nucIdentity));
+  a.touched[(size_t)(q - a.qLo) * a.nGenomes + g] = 1;
 }
 
 // ordered float32 sum over the bins of one (query, genome) pair (computeCoreIdentity.hpp:267-297);
@@ -676,23 +679,251 @@ void Ctx::upload_lut(int smaxNeeded)
   lutUploaded = target;
 }
 
+// ------------------------------------------------------------------ query sketch (stages A + B as an object)
+// Fragment descriptors of a piece, expanded on the device from one entry per fragment-bearing contig
+// (Map::mapQuery, computeMap.hpp:131-189: fragment i of a contig = bases [i*fragLen, (i+1)*fragLen), id seqCounter + i).
+struct FragSrc {
+  const uint32_t *packed; const uint32_t *excPos; const uint8_t *excByte;
+  int32_t nExc, firstFrag, seqBase, query;
+};
+
+__global__ void frag_table_kernel(const FragSrc *src, int32_t nSrc, int32_t F, int fragLen, SeqDesc *desc, int32_t *fragQuery, int32_t *fragSeqId)
+{
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= F) return;
+  int lo = 0, hi = nSrc - 1;                   // last source with firstFrag <= f
+  while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (src[mid].firstFrag <= f) lo = mid; else hi = mid - 1; }
+  const FragSrc sr = src[lo];
+  const int i = f - sr.firstFrag;
+  SeqDesc d; d.packed = sr.packed; d.excPos = sr.excPos; d.excByte = sr.excByte; d.nExc = sr.nExc;
+  d.startBase = i * fragLen; d.len = fragLen; d.seqId = sr.seqBase + i;                     // :173-175
+  desc[f] = d; fragQuery[f] = sr.query; fragSeqId[f] = sr.seqBase + i;
+}
+
+// sorted unique hashes of every fragment, back to back (the sort/unique kernel works in place on the raw segments)
+__global__ void compact_sketch_kernel(const uint32_t *raw, const uint32_t *rawStart, const uint32_t *cOff, int32_t F, uint32_t *out)
+{
+  const int f = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (f >= F) return;
+  const uint32_t a = rawStart[f], o = cOff[f], n = cOff[f + 1] - o;
+  for (uint32_t i = lane; i < n; i += 32) out[o + i] = raw[a + i];
+}
+
+static constexpr uint64_t FRAG_MAX = 1u << 17;       // fragments per piece
+
+QSketch *qsketch_create(Ctx *ctx, const Genome *const *queries, int32_t nq, const int32_t *queryIds)
+{
+  cudaStream_t st = ctx->stream;
+  const int k = ctx->prm.kmer_size, w = ctx->prm.window_size, fragLen = ctx->prm.frag_len;
+  if (fragLen < 1 || fragLen > 60000) fail(BANI_ERR_LIMIT, "fragment length %d outside the supported range [1, 60000]", fragLen);
+  auto qs = std::make_unique<QSketch>();
+  qs->device = ctx->device; qs->k = k; qs->w = w; qs->fragLen = fragLen;
+  qs->queryId.resize(nq); qs->totalFragments.assign(nq, 0);
+  for (int i = 0; i < nq; i++) qs->queryId[i] = queryIds ? queryIds[i] : i;
+
+  int q0 = 0;
+  while (q0 < nq) {
+    // ---- fragment sources of this piece (Map::mapQuery, computeMap.hpp:131-189)
+    std::vector<FragSrc> src;
+    int64_t F64 = 0;
+    int q1 = q0;
+    while (q1 < nq) {
+      const Genome *Q = queries[q1];
+      if (!Q) fail(BANI_ERR_ARG, "null genome handle");
+      if (Q->device != ctx->device) fail(BANI_ERR_ARG, "genome lives on another device");
+      uint64_t nf = 0;
+      for (int c = 0; c < Q->nContigs; c++) { int L = Q->len[c]; if (!(L < w || L < k || L < fragLen)) nf += L / fragLen; }
+      if (q1 > q0 && (uint64_t)F64 + nf > FRAG_MAX) break;
+      int32_t seqCounter = 0;
+      for (int c = 0; c < Q->nContigs; c++) {
+        const int L = Q->len[c];
+        if (L < w || L < k || L < fragLen) continue;                 // :138
+        const int fc = L / fragLen;                                  // :152
+        FragSrc sr;
+        sr.packed = Q->packed.p + Q->wordOff[c];
+        sr.nExc = (int32_t)(Q->excOff[c + 1] - Q->excOff[c]);
+        sr.excPos = sr.nExc ? Q->excPos.p + Q->excOff[c] : nullptr;
+        sr.excByte = sr.nExc ? Q->excByte.p + Q->excOff[c] : nullptr;
+        sr.firstFrag = (int32_t)F64; sr.seqBase = seqCounter; sr.query = q1 - q0;
+        src.push_back(sr);
+        F64 += fc; seqCounter += fc;
+      }
+      qs->totalFragments[q1] = (uint64_t)seqCounter;                 // :188-189
+      q1++;
+    }
+    if (F64 > 0x7ffffff0ll) fail(BANI_ERR_LIMIT, "a query genome has more than 2^31 fragments");
+    auto pc = std::make_unique<QPiece>();
+    pc->q0 = q0; pc->nq = q1 - q0; pc->F = (int32_t)F64;
+    const int32_t F = pc->F;
+    if (F > 0) {
+      BANI_SCRATCH(FragSrc, d_src, src.size());
+      BANI_CUDA(cudaMemcpyAsync(d_src.p, src.data(), sizeof(FragSrc) * src.size(), cudaMemcpyHostToDevice, st));
+      BANI_SCRATCH(SeqDesc, d_desc, F);
+      pc->fragQuery.alloc(F, st); pc->fragSeqId.alloc(F, st);
+      frag_table_kernel<<<nblk(F), 256, 0, st>>>(d_src.p, (int32_t)src.size(), F, fragLen, d_desc.p, pc->fragQuery.p, pc->fragSeqId.p);
+      ctx->launches++;
+
+      // ---- A: fragment sketches
+      View<uint32_t> rawHash;
+      BANI_SCRATCH(uint32_t, rawStart, (size_t)F + 1);
+      uint64_t perFrag = std::max(1, fragLen - k + 1);
+      uint64_t cap = std::min<uint64_t>((uint64_t)F * perFrag, (uint64_t)F * (uint64_t)(2.6 * fragLen / (w + 1) + 64));
+      uint64_t T = 0;
+      for (int attempt = 0; attempt < 2; attempt++) {
+        if (cap > 0xfffffff0ull) fail(BANI_ERR_LIMIT, "query chunk produces more than 2^32 minimizers");
+        rawHash = ctx->view<uint32_t>(BANI_SLOT_ID, std::max<uint64_t>(cap, 1));
+        Stage sg(ctx, "q_sketch", (double)F * fragLen / 4.0);
+        T = sketch_sequences(ctx, d_desc.p, F, nullptr, fragLen, rawHash.p, nullptr, nullptr, cap, rawStart.p);
+        sg.bytes((double)F * fragLen / 4.0 + 4.0 * (double)T);
+        if (T <= cap) break;
+        cap = T;
+      }
+
+      // ---- B: sorted unique hashes per fragment, then packed back to back
+      pc->sCount.alloc(F, st); pc->segStart.alloc((size_t)F + 1, st);
+      DevBuf<int> d_flags(2, st);
+      BANI_CUDA(cudaMemsetAsync(d_flags.p, 0, 8, st));
+      unsigned long long T2 = 0;
+      { Stage sg(ctx, "q_sort_unique", 8.0 * T);
+        sort_unique_kernel<<<F, SU_THREADS, 0, st>>>(rawHash.p, rawStart.p, F, pc->sCount.p, d_flags.p, d_flags.p + 1); ctx->launches++;
+        BANI_SCRATCH(uint32_t, cnt1, (size_t)F + 1);
+        BANI_CUDA(cudaMemcpyAsync(cnt1.p, pc->sCount.p, 4 * (size_t)F, cudaMemcpyDeviceToDevice, st));
+        BANI_CUDA(cudaMemsetAsync(cnt1.p + F, 0, 4, st));
+        size_t tb = cub_scan_u32_temp((size_t)F + 1);
+        BANI_SCRATCH(uint8_t, tmp, tb);
+        cub_exclusive_sum_u32(tmp.p, tb, cnt1.p, pc->segStart.p, (size_t)F + 1, st);
+        int hflags[2]; uint32_t t2 = 0;
+        BANI_CUDA(cudaMemcpyAsync(hflags, d_flags.p, 8, cudaMemcpyDeviceToHost, st));
+        BANI_CUDA(cudaMemcpyAsync(&t2, pc->segStart.p + F, 4, cudaMemcpyDeviceToHost, st));
+        BANI_CUDA(cudaStreamSynchronize(st));
+        if (hflags[1]) fail(BANI_ERR_LIMIT, "a query fragment has more than %d minimizers", SU_CAP);
+        pc->smax = hflags[0]; T2 = t2;
+        pc->fragHash.alloc(std::max<uint64_t>(T2, 1), st);
+        compact_sketch_kernel<<<nblk((uint64_t)F * 32), 256, 0, st>>>(rawHash.p, rawStart.p, pc->segStart.p, F, pc->fragHash.p); ctx->launches++; }
+      pc->T = T2;
+      BANI_CUDA(cudaGetLastError());
+      BANI_CUDA(cudaStreamSynchronize(st));          // src / scratch are reused by the next piece
+    }
+    qs->F += pc->F; qs->T += pc->T;
+    qs->pieces.push_back(std::move(pc));
+    q0 = q1;
+  }
+  return qs.release();
+}
+
+// ---- export / import: one flat DEVICE buffer, so that a query sketch can travel between GPUs (NCCL all-gather)
+//   [u64 x 8: magic, nPieces, nQueries, k, w, fragLen, totalBytes, 0]
+//   [nQueries x {i32 queryId, i32 pad, u64 totalFragments}]   [nPieces x u64 x 6: F, T, smax, q0, nq, 0]
+//   per piece, each array padded to 16 bytes: segStart[F+1] sCount[F] fragQuery[F] fragSeqId[F] fragHash[T]
+static inline uint64_t pad16(uint64_t b) { return (b + 15) & ~15ull; }
+static constexpr uint64_t QS_MAGIC = 0x42414e4951534b31ull;
+
+uint64_t qsketch_export_bytes(const QSketch *qs)
+{
+  uint64_t b = 64 + pad16(16ull * qs->queryId.size()) + 48ull * qs->pieces.size();
+  for (const auto &pc : qs->pieces)
+    if (pc->F > 0) b += pad16(4ull * (pc->F + 1)) + 3 * pad16(4ull * pc->F) + pad16(4ull * std::max<uint64_t>(pc->T, 1));
+  return b;
+}
+
+void qsketch_export(Ctx *ctx, const QSketch *qs, void *devBuf, uint64_t cap)
+{
+  cudaStream_t st = ctx->stream;
+  const uint64_t total = qsketch_export_bytes(qs);
+  if (cap < total) fail(BANI_ERR_ARG, "export buffer too small: %llu < %llu bytes", (unsigned long long)cap, (unsigned long long)total);
+  const uint64_t nQ = qs->queryId.size(), nP = qs->pieces.size();
+  const uint64_t hdrBytes = 64 + pad16(16 * nQ) + 48 * nP;
+  std::vector<uint8_t> h(hdrBytes, 0);
+  uint64_t *h64 = (uint64_t *)h.data();
+  h64[0] = QS_MAGIC; h64[1] = nP; h64[2] = nQ; h64[3] = (uint64_t)qs->k; h64[4] = (uint64_t)qs->w; h64[5] = (uint64_t)qs->fragLen; h64[6] = total;
+  for (uint64_t i = 0; i < nQ; i++) {
+    int32_t *e = (int32_t *)(h.data() + 64 + 16 * i);
+    e[0] = qs->queryId[i]; *(uint64_t *)(e + 2) = qs->totalFragments[i];
+  }
+  uint64_t *ph = (uint64_t *)(h.data() + 64 + pad16(16 * nQ));
+  for (uint64_t i = 0; i < nP; i++) {
+    const QPiece &pc = *qs->pieces[i];
+    ph[6 * i + 0] = (uint64_t)pc.F; ph[6 * i + 1] = pc.T; ph[6 * i + 2] = (uint64_t)pc.smax; ph[6 * i + 3] = (uint64_t)pc.q0; ph[6 * i + 4] = (uint64_t)pc.nq;
+  }
+  uint8_t *d = (uint8_t *)devBuf;
+  BANI_CUDA(cudaMemcpyAsync(d, h.data(), hdrBytes, cudaMemcpyHostToDevice, st));
+  uint64_t o = hdrBytes;
+  auto put = [&](const void *p, uint64_t bytes) { BANI_CUDA(cudaMemcpyAsync(d + o, p, bytes, cudaMemcpyDeviceToDevice, st)); o += pad16(bytes); };
+  for (const auto &pc : qs->pieces) {
+    if (pc->F == 0) continue;
+    put(pc->segStart.p, 4ull * (pc->F + 1)); put(pc->sCount.p, 4ull * pc->F); put(pc->fragQuery.p, 4ull * pc->F);
+    put(pc->fragSeqId.p, 4ull * pc->F); put(pc->fragHash.p, 4ull * std::max<uint64_t>(pc->T, 1));
+  }
+  BANI_CUDA(cudaStreamSynchronize(st));              // h must outlive the copy
+}
+
+QSketch *qsketch_import(Ctx *ctx, const void *devBuf, uint64_t bytes)
+{
+  cudaStream_t st = ctx->stream;
+  if (bytes < 64) fail(BANI_ERR_ARG, "not a query sketch buffer");
+  uint64_t h0[8];
+  BANI_CUDA(cudaMemcpyAsync(h0, devBuf, 64, cudaMemcpyDeviceToHost, st));
+  BANI_CUDA(cudaStreamSynchronize(st));
+  if (h0[0] != QS_MAGIC || h0[6] > bytes) fail(BANI_ERR_ARG, "not a query sketch buffer (or truncated)");
+  if ((int)h0[3] != ctx->prm.kmer_size || (int)h0[4] != ctx->prm.window_size || (int)h0[5] != ctx->prm.frag_len)
+    fail(BANI_ERR_ARG, "query sketch was built with other parameters (k %d w %d fragLen %d)", (int)h0[3], (int)h0[4], (int)h0[5]);
+  const uint64_t nP = h0[1], nQ = h0[2];
+  const uint64_t hdrBytes = 64 + pad16(16 * nQ) + 48 * nP;
+  std::vector<uint8_t> h(hdrBytes);
+  BANI_CUDA(cudaMemcpyAsync(h.data(), devBuf, hdrBytes, cudaMemcpyDeviceToHost, st));
+  BANI_CUDA(cudaStreamSynchronize(st));
+  auto qs = std::make_unique<QSketch>();
+  qs->device = ctx->device; qs->k = (int)h0[3]; qs->w = (int)h0[4]; qs->fragLen = (int)h0[5];
+  qs->queryId.resize(nQ); qs->totalFragments.resize(nQ);
+  for (uint64_t i = 0; i < nQ; i++) {
+    const int32_t *e = (const int32_t *)(h.data() + 64 + 16 * i);
+    qs->queryId[i] = e[0]; qs->totalFragments[i] = *(const uint64_t *)(e + 2);
+  }
+  const uint64_t *ph = (const uint64_t *)(h.data() + 64 + pad16(16 * nQ));
+  const uint8_t *d = (const uint8_t *)devBuf;
+  uint64_t o = hdrBytes;
+  for (uint64_t i = 0; i < nP; i++) {
+    auto pc = std::make_unique<QPiece>();
+    pc->F = (int32_t)ph[6 * i]; pc->T = ph[6 * i + 1]; pc->smax = (int)ph[6 * i + 2]; pc->q0 = (int)ph[6 * i + 3]; pc->nq = (int)ph[6 * i + 4];
+    if (pc->F > 0) {
+      auto get = [&](void *p, uint64_t b) { if (o + b > bytes) fail(BANI_ERR_ARG, "query sketch buffer truncated");
+                                             BANI_CUDA(cudaMemcpyAsync(p, d + o, b, cudaMemcpyDeviceToDevice, st)); o += pad16(b); };
+      pc->segStart.alloc((size_t)pc->F + 1, st); pc->sCount.alloc(pc->F, st); pc->fragQuery.alloc(pc->F, st); pc->fragSeqId.alloc(pc->F, st);
+      pc->fragHash.alloc(std::max<uint64_t>(pc->T, 1), st);
+      get(pc->segStart.p, 4ull * (pc->F + 1)); get(pc->sCount.p, 4ull * pc->F); get(pc->fragQuery.p, 4ull * pc->F);
+      get(pc->fragSeqId.p, 4ull * pc->F); get(pc->fragHash.p, 4ull * std::max<uint64_t>(pc->T, 1));
+    }
+    qs->F += pc->F; qs->T += pc->T;
+    qs->pieces.push_back(std::move(pc));
+  }
+  BANI_CUDA(cudaStreamSynchronize(st));
+  return qs.release();
+}
+
+// ------------------------------------------------------------------ host orchestration of stages C..H
 void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_t nq,
+                 bool wantRows, bool wantCgi, MapOutput &out)
+{
+  std::unique_ptr<QSketch> qs(qsketch_create(ctx, queries, nq, nullptr));
+  const QSketch *one = qs.get();
+  qsketch_map(ctx, ix, &one, 1, wantRows, wantCgi, out);
+  out.totalQueryFragments = qs->totalFragments;
+}
+
+void qsketch_map(Ctx *ctx, const Index *ix, const QSketch *const *sketches, int32_t nSketches,
                  bool wantRows, bool wantCgi, MapOutput &out)
 {
   cudaStream_t st = ctx->stream;
   const int k = ctx->prm.kmer_size, w = ctx->prm.window_size, fragLen = ctx->prm.frag_len;
   const float pid = ctx->prm.perc_identity;
   if (ix->device != ctx->device) fail(BANI_ERR_ARG, "index lives on another device");
-  if (fragLen < 1 || fragLen > 60000) fail(BANI_ERR_LIMIT, "fragment length %d outside the supported range [1, 60000]", fragLen);
   if (wantCgi && fragLen <= 20) fail(BANI_ERR_ARG, "fragment length must exceed 20 for the identity reduction");
   const int cmw = fragLen - (w - 1) - (k - 1);         // computeMap.hpp:427
-  out.totalQueryFragments.assign(nq, 0);
   out.ctr = bani_map_counters{};
   const int nG = ix->nGenomes;
 
-  // chunk the query list: bounded fragment count and bounded 2-way table
-  const uint64_t FRAG_MAX = 1u << 17;
-  uint64_t qMaxByTable = nq;
+  // the 2-way table holds a bounded number of queries at a time
+  uint64_t qMaxByTable = 1u << 30;
   if (wantCgi && ix->totalBins) qMaxByTable = std::max<uint64_t>(1, ((uint64_t)3 << 30) / (4 * ix->totalBins));
 
   DevBuf<uint32_t> table; DevBuf<uint8_t> touched; DevBuf<int32_t> d_gce;
@@ -702,82 +933,30 @@ void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_
     if (nG) BANI_CUDA(cudaMemcpyAsync(d_gce.p, ix->seqsByFile.data(), 4 * (size_t)nG, cudaMemcpyHostToDevice, st));
   }
 
-  int q0 = 0;
-  while (q0 < nq) {
-    // ---- fragment table of this chunk (Map::mapQuery, computeMap.hpp:131-189)
-    std::vector<SeqDesc> desc; std::vector<int32_t> fragQuery, flen;
-    int q1 = q0;
-    while (q1 < nq && (uint64_t)(q1 - q0) < qMaxByTable) {
-      const Genome *Q = queries[q1];
-      if (!Q) fail(BANI_ERR_ARG, "null genome handle");
-      if (Q->device != ctx->device) fail(BANI_ERR_ARG, "genome lives on another device");
-      uint64_t nf = 0;
-      for (int c = 0; c < Q->nContigs; c++) { int L = Q->len[c]; if (!(L < w || L < k || L < fragLen)) nf += L / fragLen; }
-      if (q1 > q0 && desc.size() + nf > FRAG_MAX) break;
-      int32_t seqCounter = 0;
-      for (int c = 0; c < Q->nContigs; c++) {
-        const int L = Q->len[c];
-        if (L < w || L < k || L < fragLen) continue;                 // :138
-        const int fc = L / fragLen;                                  // :152
-        for (int i = 0; i < fc; i++) {
-          SeqDesc d;
-          d.packed = Q->packed.p + Q->wordOff[c];
-          d.nExc = (int32_t)(Q->excOff[c + 1] - Q->excOff[c]);
-          d.excPos = d.nExc ? Q->excPos.p + Q->excOff[c] : nullptr;
-          d.excByte = d.nExc ? Q->excByte.p + Q->excOff[c] : nullptr;
-          d.startBase = i * fragLen; d.len = fragLen; d.seqId = seqCounter + i;   // :173-175
-          desc.push_back(d); fragQuery.push_back(q1 - q0); flen.push_back(fragLen);
-        }
-        seqCounter += fc;
-      }
-      out.totalQueryFragments[q1] = (uint64_t)seqCounter;            // :188-189
-      q1++;
-    }
-    const int nQc = q1 - q0;
-    const int32_t F = (int32_t)desc.size();
+  for (int32_t si = 0; si < nSketches; si++) {
+   const QSketch *qs = sketches[si];
+   if (!qs) fail(BANI_ERR_ARG, "null query sketch");
+   if (qs->device != ctx->device) fail(BANI_ERR_ARG, "query sketch lives on another device");
+   if (qs->k != k || qs->w != w || qs->fragLen != fragLen) fail(BANI_ERR_ARG, "query sketch was built with other parameters");
+   for (const auto &pcp : qs->pieces) {
+    const QPiece &pc = *pcp;
+    const int nQc = pc.nq, q0 = pc.q0;
+    const int32_t F = pc.F;
+    const uint64_t T = pc.T;
+    const int smax = pc.smax;
     out.ctr.fragments += F;
+    View<uint32_t> fragHash; fragHash.p = pc.fragHash.p; fragHash.n = T;
+    View<uint32_t> segStart; segStart.p = pc.segStart.p; segStart.n = (size_t)F + 1;
+    View<int32_t> sCount; sCount.p = pc.sCount.p; sCount.n = F;
+    View<int32_t> d_fragQuery; d_fragQuery.p = pc.fragQuery.p; d_fragQuery.n = F;
+    View<int32_t> d_fragSeqId; d_fragSeqId.p = pc.fragSeqId.p; d_fragSeqId.n = F;
 
     std::vector<int32_t> hCount; std::vector<float> hIdent;
     if (wantCgi) { hCount.assign((size_t)nQc * nG, 0); hIdent.assign((size_t)nQc * nG, 0.f); }
 
     if (F > 0 && ix->M > 0) {
-      BANI_SCRATCH(SeqDesc, d_desc, F);
-      BANI_CUDA(cudaMemcpyAsync(d_desc.p, desc.data(), sizeof(SeqDesc) * (size_t)F, cudaMemcpyHostToDevice, st));
-      BANI_SCRATCH(int32_t, d_fragQuery, F);
-      BANI_SCRATCH(int32_t, d_fragSeqId, F);
-      BANI_CUDA(cudaMemcpyAsync(d_fragQuery.p, fragQuery.data(), 4 * (size_t)F, cudaMemcpyHostToDevice, st));
-      { std::vector<int32_t> ids(F); for (int i = 0; i < F; i++) ids[i] = desc[i].seqId;
-        BANI_CUDA(cudaMemcpyAsync(d_fragSeqId.p, ids.data(), 4 * (size_t)F, cudaMemcpyHostToDevice, st));
-        BANI_CUDA(cudaStreamSynchronize(st)); }
-
-      // ---- A: fragment sketches
-      View<uint32_t> fragHash;
-      BANI_SCRATCH(uint32_t, segStart, (size_t)F + 1);
-      uint64_t perFrag = std::max(1, fragLen - k + 1);
-      uint64_t cap = std::min<uint64_t>((uint64_t)F * perFrag, (uint64_t)F * (uint64_t)(2.6 * fragLen / (w + 1) + 64));
-      uint64_t T = 0;
-      for (int attempt = 0; attempt < 2; attempt++) {
-        if (cap > 0xfffffff0ull) fail(BANI_ERR_LIMIT, "query chunk produces more than 2^32 minimizers");
-        fragHash = ctx->view<uint32_t>(__LINE__, std::max<uint64_t>(cap, 1));
-        Stage sg(ctx, "q_sketch", (double)F * fragLen / 4.0);
-        T = sketch_sequences(ctx, d_desc.p, F, flen.data(), fragHash.p, nullptr, nullptr, cap, segStart.p);
-        sg.bytes((double)F * fragLen / 4.0 + 4.0 * (double)T);
-        if (T <= cap) break;
-        cap = T;
-      }
-
-      // ---- B: sorted unique hashes per fragment
-      BANI_SCRATCH(int32_t, sCount, F);
-      DevBuf<int> d_flags(2, st);
-      BANI_CUDA(cudaMemsetAsync(d_flags.p, 0, 8, st));
-      { Stage sg(ctx, "q_sort_unique", 8.0 * T);
-        sort_unique_kernel<<<F, SU_THREADS, 0, st>>>(fragHash.p, segStart.p, F, sCount.p, d_flags.p, d_flags.p + 1); ctx->launches++; }
-      int hflags[2];
-      BANI_CUDA(cudaMemcpyAsync(hflags, d_flags.p, 8, cudaMemcpyDeviceToHost, st));
-      BANI_CUDA(cudaStreamSynchronize(st));
-      if (hflags[1]) fail(BANI_ERR_LIMIT, "a query fragment has more than %d minimizers", SU_CAP);
-      const int smax = hflags[0];
       ctx->upload_lut(smax);
+      out.ctr.sum_s += T;
 
       if (T > 0 && smax > 0) {
         // ---- C: lookup
@@ -794,8 +973,6 @@ void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_
         unsigned long long N = 0;
         BANI_CUDA(cudaMemcpyAsync(&N, hitOff.p + T, 8, cudaMemcpyDeviceToHost, st));
         BANI_CUDA(cudaStreamSynchronize(st));
-        { std::vector<int32_t> hs(F); BANI_CUDA(cudaMemcpy(hs.data(), sCount.p, 4 * (size_t)F, cudaMemcpyDeviceToHost));
-          for (int i = 0; i < F; i++) out.ctr.sum_s += hs[i]; }
         out.ctr.hits += N;
         if (N > 0xfffffff0ull) fail(BANI_ERR_LIMIT, "query chunk gathers more than 2^32 index hits");
 
@@ -993,9 +1170,10 @@ void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_
                 BANI_CUDA(cudaStreamSynchronize(st));
               }
               if (wantCgi) {
-                // ---- H: CGI
-                if ((uint64_t)nQc > tableQ) {
-                  tableQ = std::min<uint64_t>(qMaxByTable, std::max<uint64_t>(nQc, 1));
+                // ---- H: CGI, at most tableQ queries of the piece per pass over the rows
+                const uint64_t needQ = std::min<uint64_t>(qMaxByTable, std::max<uint64_t>(nQc, 1));
+                if (needQ > tableQ) {
+                  tableQ = needQ;
                   table.alloc((size_t)tableQ * ix->totalBins, st); touched.alloc((size_t)tableQ * std::max(nG, 1), st);
                   BANI_CUDA(cudaMemsetAsync(table.p, 0, table.bytes(), st));
                   BANI_CUDA(cudaMemsetAsync(touched.p, 0, touched.bytes(), st));
@@ -1006,10 +1184,15 @@ void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_
                 BANI_SCRATCH(int32_t, oCount, (size_t)nQc * nG);
                 DevBuf<float> oIdent((size_t)nQc * nG, st);
                 { Stage sg(ctx, "cgi", 48.0 * R);
-                  cgi_scatter_kernel<<<nblk(R), 256, 0, st>>>(ca);
-                  ctx->launches++;
-                  cgi_sum_kernel<<<nblk((uint64_t)nQc * nG), 256, 0, st>>>(table.p, touched.p, ix->contigBinOff.p, d_gce.p,
-                                                                          ix->totalBins, nG, nQc, oCount.p, oIdent.p); ctx->launches++; }
+                  for (int qa = 0; qa < nQc; qa += (int)tableQ) {
+                    const int nPass = std::min<int>((int)tableQ, nQc - qa);
+                    ca.qLo = qa; ca.qHi = qa + nPass;
+                    cgi_scatter_kernel<<<nblk(R), 256, 0, st>>>(ca);
+                    ctx->launches++;
+                    cgi_sum_kernel<<<nblk((uint64_t)nPass * nG), 256, 0, st>>>(table.p, touched.p, ix->contigBinOff.p, d_gce.p,
+                                                                             ix->totalBins, nG, nPass, oCount.p + (size_t)qa * nG, oIdent.p + (size_t)qa * nG);
+                    ctx->launches++;
+                  } }
                 BANI_CUDA(cudaMemcpyAsync(hCount.data(), oCount.p, 4 * (size_t)nQc * nG, cudaMemcpyDeviceToHost, st));
                 BANI_CUDA(cudaMemcpyAsync(hIdent.data(), oIdent.p, 4 * (size_t)nQc * nG, cudaMemcpyDeviceToHost, st));
                 BANI_CUDA(cudaStreamSynchronize(st));
@@ -1026,14 +1209,14 @@ void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_
         for (int g = 0; g < nG; g++) {
           const int32_t cnt = hCount[(size_t)q * nG + g];
           if (cnt > 0) {
-            bani_cgi_result r; r.refGenomeId = g; r.qryGenomeId = q0 + q; r.countSeq = cnt;
-            r.totalQueryFragments = (int32_t)out.totalQueryFragments[q0 + q];       // cgid_types.hpp:73 (int)
+            bani_cgi_result r; r.refGenomeId = g; r.qryGenomeId = qs->queryId[q0 + q]; r.countSeq = cnt;
+            r.totalQueryFragments = (int32_t)qs->totalFragments[q0 + q];            // cgid_types.hpp:73 (int)
             r.identity = hIdent[(size_t)q * nG + g];
             out.cgi.push_back(r);
           }
         }
     }
-    q0 = q1;
+   }
   }
 }
 

@@ -42,6 +42,7 @@ static constexpr int SK_KEYS = SK_SLOTS + SK_SLOTS / 16;
 struct SketchArgs {
   const SeqDesc *desc; const uint32_t *tileOff;   // nSeq+1
   int32_t nSeq; uint32_t nTiles;
+  int32_t uniformTiles;             // > 0: every sequence has this many tiles (query fragments): no tileOff table
   int k, w, tileLen;
   uint32_t *o_hash; int32_t *o_wpos; int32_t *o_seqId; uint64_t cap;
   uint32_t *o_segStart;
@@ -175,11 +176,14 @@ sketch_kernel(const SketchArgs a)
   const int k = KT > 0 ? KT : a.k, w = a.w;
 
   // ---- which sequence / tile
-  int lo = 0, hi = a.nSeq - 1;
-  while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (a.tileOff[mid] <= tile) lo = mid; else hi = mid - 1; }
-  const int seq = lo;
+  int seq, t0;
+  if (a.uniformTiles > 0) { seq = (int)(tile / (uint32_t)a.uniformTiles); t0 = (int)(tile % (uint32_t)a.uniformTiles) * a.tileLen; }
+  else {
+    int lo = 0, hi = a.nSeq - 1;
+    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (a.tileOff[mid] <= tile) lo = mid; else hi = mid - 1; }
+    seq = lo; t0 = (int)(tile - a.tileOff[seq]) * a.tileLen;
+  }
   const SeqDesc d = a.desc[seq];
-  const int t0 = (int)(tile - a.tileOff[seq]) * a.tileLen;
   const int npos = d.len - k + 1;                               // may be <= 0
   const int hs = max(0, t0 - 2 * (w - 1));                      // first hashed position
   const int he = min(npos, t0 + a.tileLen);                     // one past the last hashed position
@@ -345,7 +349,7 @@ static void launch_sketch(const SketchArgs &a, cudaStream_t st)
   else             sketch_kernel<KT, 1><<<a.nTiles, SK_THREADS, 0, st>>>(a);
 }
 
-uint64_t sketch_sequences(Ctx *ctx, const SeqDesc *d_desc, int32_t nSeq, const int32_t *h_len,
+uint64_t sketch_sequences(Ctx *ctx, const SeqDesc *d_desc, int32_t nSeq, const int32_t *h_len, int32_t uniformLen,
                           uint32_t *o_hash, int32_t *o_wpos, int32_t *o_seqId, uint64_t cap,
                           uint32_t *o_segStart)
 {
@@ -358,21 +362,32 @@ uint64_t sketch_sequences(Ctx *ctx, const SeqDesc *d_desc, int32_t nSeq, const i
     return 0;
   }
   const int tileLen = (SK_SLOTS - 2 * (w - 1)) & ~15;
-  std::vector<uint32_t> tileOff(nSeq + 1);
   uint64_t tiles = 0;
-  for (int i = 0; i < nSeq; i++) {
-    tileOff[i] = (uint32_t)tiles;
-    int64_t npos = (int64_t)h_len[i] - k + 1;
-    tiles += npos <= 0 ? 1 : (uint64_t)((npos + tileLen - 1) / tileLen);
+  int32_t uniformTiles = 0;
+  DevBuf<uint32_t> d_tileOff;
+  std::vector<uint32_t> tileOff;
+  if (uniformLen > 0) {
+    // all sequences have the same length (query fragments): tile -> sequence is a division
+    const int64_t npos = (int64_t)uniformLen - k + 1;
+    uniformTiles = npos <= 0 ? 1 : (int32_t)((npos + tileLen - 1) / tileLen);
+    tiles = (uint64_t)uniformTiles * (uint64_t)nSeq;
     if (tiles > 0x7fffffffull) fail(BANI_ERR_LIMIT, "too many sketch tiles in one launch");
+  } else {
+    tileOff.resize(nSeq + 1);
+    for (int i = 0; i < nSeq; i++) {
+      tileOff[i] = (uint32_t)tiles;
+      int64_t npos = (int64_t)h_len[i] - k + 1;
+      tiles += npos <= 0 ? 1 : (uint64_t)((npos + tileLen - 1) / tileLen);
+      if (tiles > 0x7fffffffull) fail(BANI_ERR_LIMIT, "too many sketch tiles in one launch");
+    }
+    tileOff[nSeq] = (uint32_t)tiles;
+    d_tileOff.alloc(nSeq + 1, st);
+    BANI_CUDA(cudaMemcpyAsync(d_tileOff.p, tileOff.data(), 4 * (size_t)(nSeq + 1), cudaMemcpyHostToDevice, st));
   }
-  tileOff[nSeq] = (uint32_t)tiles;
-  DevBuf<uint32_t> d_tileOff(nSeq + 1, st);
-  BANI_CUDA(cudaMemcpyAsync(d_tileOff.p, tileOff.data(), 4 * (size_t)(nSeq + 1), cudaMemcpyHostToDevice, st));
   DevBuf<unsigned long long> state(tiles + 1, st);
   BANI_CUDA(cudaMemsetAsync(state.p, 0, 8 * (tiles + 1), st));
   SketchArgs a;
-  a.desc = d_desc; a.tileOff = d_tileOff.p; a.nSeq = nSeq; a.nTiles = (uint32_t)tiles;
+  a.desc = d_desc; a.tileOff = d_tileOff.p; a.nSeq = nSeq; a.nTiles = (uint32_t)tiles; a.uniformTiles = uniformTiles;
   a.k = k; a.w = w; a.tileLen = tileLen;
   a.o_hash = o_hash; a.o_wpos = o_wpos; a.o_seqId = o_seqId; a.cap = cap; a.o_segStart = o_segStart;
   a.tileState = state.p; a.o_total = state.p + tiles;

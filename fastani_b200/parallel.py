@@ -3,8 +3,10 @@
 This is exactly the reference's threading rule lifted to GPUs (src/cgi/include/
 computeCoreIdentity.hpp:457-487): shard g owns references j with j % G == g, every shard maps
 ALL queries against its own index, results of different shards are disjoint, and a local
-reference id becomes global as local * G + g.  The only exchange is the final gather of the
-dense per-pair tables (count int32, identity float32); no data-path collective exists.
+reference id becomes global as local * G + g.  Two exchanges: (1) the query sketches -- rank r sketches the
+queries r, r+G, ... once and the sorted fragment sketches (~0.33 B per query base) are all-gathered over NCCL,
+so the query-side work is not repeated on every rank; (2) the final gather of the dense per-pair tables
+(count int32, identity float32).
 """
 import numpy as np
 
@@ -60,3 +62,26 @@ def gather_tables(cnt_local, idn_local, n_refs, world, rank, dist=None, device=N
     dist.all_gather(gc, tc); dist.all_gather(gi, ti)
     tables = [(gc[g].cpu().numpy(), gi[g].cpu().numpy()) for g in range(world)]
     return merge_shards(tables, n_queries, n_refs, world)
+
+
+def exchange_query_sketches(ctx, mine, world, rank, dist, device):
+    """All-gather of the ranks' QuerySketch objects: each is packed into a flat device buffer (bani_qsketch_export),
+    the buffers travel in one padded NCCL all-gather, and the peers' sketches are rebuilt on this device
+    (bani_qsketch_import).  Returns the `world` sketches in rank order (this rank's own object included)."""
+    import torch
+    from .api import QuerySketch
+    nbytes = mine.info()["export_bytes"]
+    sizes = torch.zeros(world, dtype=torch.int64, device=device)
+    sizes[rank] = nbytes
+    dist.all_reduce(sizes)
+    sizes = [int(x) for x in sizes.cpu()]
+    width = (max(sizes) + 255) // 256 * 256
+    send = torch.empty(width, dtype=torch.uint8, device=device)
+    mine.export_to(send.data_ptr(), width)              # synchronises the library's stream: the bytes are in place
+    recv = torch.empty(world * width, dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(recv, send)
+    torch.cuda.synchronize(device)
+    out = []
+    for r in range(world):
+        out.append(mine if r == rank else QuerySketch.from_device_buffer(ctx, recv.data_ptr() + r * width, sizes[r]))
+    return out

@@ -181,6 +181,25 @@ BANI_API int  bani_map_cgi(bani_ctx *ctx, const bani_index *ix, bani_genome *con
                            bani_cgi_result **results, uint64_t *n_results,
                            uint64_t *total_query_fragments, bani_map_counters *counters);
 
+/* ---- query sketch: the first half of HP2 as an object -------------------------
+ * Map::doL1Mapping, computeMap.hpp:252-276: the sorted unique minimizer hashes of every 3 kb fragment of a
+ * set of query genomes.  bani_map_cgi() builds it internally; building it separately lets a multi-GPU run
+ * sketch each query ONCE (rank r sketches queries r, r+N, ...), move the sketches between GPUs
+ * (export -> NCCL all-gather -> import; a sketch is ~0.33 bytes per query base) and map every sketch against
+ * each rank's reference shard.  query_ids[i] is reported as qryGenomeId (NULL: 0..n-1). */
+typedef struct bani_qsketch bani_qsketch;
+BANI_API int  bani_qsketch_create(bani_ctx *ctx, bani_genome *const *queries, int32_t n_queries, const int32_t *query_ids,
+                                  bani_qsketch **out);
+BANI_API void bani_qsketch_destroy(bani_qsketch *qs);
+BANI_API int  bani_qsketch_info(const bani_qsketch *qs, int32_t *n_queries, uint64_t *n_fragments, uint64_t *n_hashes,
+                                uint64_t *export_bytes);
+/* Pack into / rebuild from one flat DEVICE buffer (cap >= export_bytes; 16-byte aligned). */
+BANI_API int  bani_qsketch_export(bani_ctx *ctx, const bani_qsketch *qs, void *device_buf, uint64_t cap);
+BANI_API int  bani_qsketch_import(bani_ctx *ctx, const void *device_buf, uint64_t bytes, bani_qsketch **out);
+/* bani_map_cgi for prebuilt sketches (all on this context's device); results ordered by (sketch, query, refGenomeId). */
+BANI_API int  bani_map_cgi_sketch(bani_ctx *ctx, const bani_index *ix, const bani_qsketch *const *sketches, int32_t n_sketches,
+                                  bani_cgi_result **results, uint64_t *n_results, bani_map_counters *counters);
+
 BANI_API void bani_free(void *p);
 
 /* ---- bench utilities -------------------------------------------------------

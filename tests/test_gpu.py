@@ -318,3 +318,33 @@ def test_cli_many_to_many_lists_match_the_python_host(tmp_path):
     # host CGI path (--visualize) gives the same table
     _cli_run(["--ql", "ql.txt", "--rl", "rl.txt", "-o", "vis.txt", "--visualize", "--gpus", "1", "--minFraction", "0.1"], tmp_path)
     assert open(tmp_path / "vis.txt").read() == open(tmp_path / "out.txt").read()
+
+
+def test_query_sketch_objects_export_import_and_map():
+    """bani_qsketch_*: sketching the queries in two halves (as two ranks would), moving one half through a flat device
+    buffer, and mapping both halves against the index gives exactly compute_cgi's rows."""
+    import torch
+    genomes = _cluster_set(2, 4, 70000)
+    ctx = fb.Context(fb.Parameters())
+    hs = ctx.genomes(genomes)
+    n = len(hs)
+    sk = fb.Sketch(ctx, hs[1:])
+    want, tot, ctr = fb.compute_cgi(ctx, sk, hs)
+    even, odd = list(range(0, n, 2)), list(range(1, n, 2))
+    s0 = fb.QuerySketch(ctx, [hs[i] for i in even], even)
+    s1 = fb.QuerySketch(ctx, [hs[i] for i in odd], odd)
+    i1 = s1.info()
+    assert i1["n_queries"] == len(odd) and i1["n_fragments"] == int(sum(tot[i] for i in odd)) and i1["export_bytes"] % 16 == 0
+    buf = torch.empty(i1["export_bytes"] + 64, dtype=torch.uint8, device="cuda")
+    s1.export_to(buf.data_ptr(), buf.numel())
+    s1b = fb.QuerySketch.from_device_buffer(ctx, buf.data_ptr(), i1["export_bytes"])
+    assert s1b.info() == i1
+    got, ctr2 = fb.compute_cgi_sketched(ctx, sk, [s0, s1b])
+    key = lambda a: np.sort(a, order=["qryGenomeId", "refGenomeId"])
+    assert key(got).tobytes() == key(want).tobytes()
+    assert ctr2.as_dict() == ctr.as_dict()
+    # truncated / foreign buffers are rejected
+    with pytest.raises(fb.BaniError):
+        fb.QuerySketch.from_device_buffer(ctx, buf.data_ptr(), 32)
+    with pytest.raises(fb.BaniError):
+        fb.QuerySketch.from_device_buffer(fb.Context(fb.Parameters(kmerSize=21)), buf.data_ptr(), i1["export_bytes"])
