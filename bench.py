@@ -259,7 +259,7 @@ def main_ours(a):
             res, tot, ctr = fb.compute_cgi(ctx, sk, genomes)
             d2h = res.nbytes + tot.nbytes
         else:
-            mine = fb.QuerySketch(ctx, [genomes[slot[i]] for i in my_qrys], my_qrys)
+            mine = fb.QuerySketch(ctx, [genomes[slot[i]] for i in my_qrys], my_qrys, hint=sk)
             sketches = parallel.exchange_query_sketches(ctx, mine, world, rank, dist, device)
             res, ctr = fb.compute_cgi_sketched(ctx, sk, sketches)
             d2h = res.nbytes

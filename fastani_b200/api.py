@@ -91,7 +91,7 @@ def load_library():
         "bani_map_genome": (C.c_int, [vp, vp, vp, P(vp), P(u64), P(u64), P(MapCounters)]),
         "bani_map_cgi": (C.c_int, [vp, vp, P(vp), i32, P(vp), P(u64), vp, P(MapCounters)]),
         "bani_device_count": (C.c_int, [P(i32)]),
-        "bani_qsketch_create": (C.c_int, [vp, P(vp), i32, vp, P(vp)]),
+        "bani_qsketch_create": (C.c_int, [vp, P(vp), i32, vp, vp, P(vp)]),
         "bani_qsketch_destroy": (None, [vp]),
         "bani_qsketch_info": (C.c_int, [vp, P(i32), P(u64), P(u64), P(u64)]),
         "bani_qsketch_export": (C.c_int, [vp, vp, vp, u64]),
@@ -388,7 +388,7 @@ class QuerySketch:
     a flat device buffer (export_to) and rebuilt on another GPU (from_device_buffer), which is what a multi-GPU
     run exchanges instead of sketching every query on every rank."""
 
-    def __init__(self, ctx, query_genomes=None, query_ids=None, _handle=None):
+    def __init__(self, ctx, query_genomes=None, query_ids=None, hint=None, _handle=None):
         self.ctx = ctx
         if _handle is not None:
             self.h = _handle
@@ -400,7 +400,8 @@ class QuerySketch:
             ids = np.ascontiguousarray(query_ids, dtype=np.int32)
             assert len(ids) == len(qs)
         h = C.c_void_p()
-        _check(ctx.lib.bani_qsketch_create(ctx.h, arr, len(qs), ids.ctypes.data if ids is not None else None, C.byref(h)))
+        _check(ctx.lib.bani_qsketch_create(ctx.h, arr, len(qs), ids.ctypes.data if ids is not None else None,
+                                           hint.h if hint is not None else None, C.byref(h)))
         self.h = h
 
     @classmethod

@@ -6,6 +6,7 @@
 // driver is only asked on a miss, and everything cached is returned to it when an allocation fails or
 // when the last context of the device goes away.  Reuse is stream-ordered: a block is only ever reused
 // on the stream it was freed on, so no event is needed.
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -27,6 +28,12 @@ size_t round_size(size_t b)
   if (b <= (1u << 20)) return (b + 4095) & ~(size_t)4095;
   return (b + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
 }
+}
+
+uint64_t next_genome_uid()
+{
+  static std::atomic<uint64_t> n(1);
+  return n++;
 }
 
 void dev_cache_flush(int dev)

@@ -358,7 +358,8 @@ int bani_map_cgi(bani_ctx *ctx, const bani_index *ix, bani_genome *const *querie
   BANI_CATCH
 }
 
-int bani_qsketch_create(bani_ctx *ctx, bani_genome *const *queries, int32_t n_queries, const int32_t *query_ids, bani_qsketch **out)
+int bani_qsketch_create(bani_ctx *ctx, bani_genome *const *queries, int32_t n_queries, const int32_t *query_ids,
+                        const bani_index *hint, bani_qsketch **out)
 {
   BANI_TRY
   if (!ctx || n_queries < 0 || (n_queries && !queries) || !out) fail(BANI_ERR_ARG, "null argument");
@@ -366,7 +367,7 @@ int bani_qsketch_create(bani_ctx *ctx, bani_genome *const *queries, int32_t n_qu
   std::vector<const Genome *> qs(n_queries);
   for (int i = 0; i < n_queries; i++) { if (!queries[i]) fail(BANI_ERR_ARG, "null genome handle"); qs[i] = &queries[i]->g; }
   std::unique_ptr<bani_qsketch> h(new bani_qsketch());
-  h->qs = qsketch_create(&ctx->c, qs.data(), n_queries, query_ids);
+  h->qs = qsketch_create(&ctx->c, qs.data(), n_queries, query_ids, hint ? hint->ix : nullptr);
   *out = h.release();
   return BANI_OK;
   BANI_CATCH

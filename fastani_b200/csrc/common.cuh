@@ -88,7 +88,10 @@ struct SeqDesc {
   int32_t seqId;            // ordinal written to the records
 };
 
+uint64_t next_genome_uid();
+
 struct Genome {
+  uint64_t uid = next_genome_uid();  // identity that survives address reuse (index membership, see Index::members)
   int device = 0;
   int32_t nContigs = 0;
   std::vector<int32_t> len;          // per contig
@@ -143,6 +146,12 @@ struct Index {
   DevBuf<uint32_t> dir;              // (1<<dirBits)+1 bucket directory over the top bits of the hash
   std::vector<int32_t> contigLen;    // host copies
   std::vector<int32_t> seqsByFile;   // cumulative contig count per genome (sequencesByFileInfo)
+  // Which genomes the index was built from (uid -> first contig ordinal) and, per hashed position, whether it was
+  // VALID (forward hash != reverse-complement hash, commonFunc.hpp:131): together with the position-ordered records
+  // this is enough to derive the fragment sketches of a member genome without hashing it again (map.cu, stage A').
+  std::map<uint64_t, int32_t> members;
+  DevBuf<uint32_t> validBits;        // bit contigBitBase[c] + p = position p of contig c is valid
+  DevBuf<unsigned long long> contigBitBase;   // nContigs (multiples of 32)
   uint64_t totalBins = 0;
 };
 
@@ -215,7 +224,8 @@ void genome_decode(Ctx *ctx, const Genome *g, int32_t contig, uint8_t *out, int6
 // (which may exceed `cap`; only the first cap are stored).
 uint64_t sketch_sequences(Ctx *ctx, const SeqDesc *d_desc, int32_t nSeq, const int32_t *h_len, int32_t uniformLen,
                           uint32_t *o_hash, int32_t *o_wpos, int32_t *o_seqId, uint64_t cap,
-                          uint32_t *o_segStart /* nSeq+1 */);
+                          uint32_t *o_segStart /* nSeq+1 */,
+                          uint32_t *o_validBits = nullptr, const unsigned long long *bitBase = nullptr);
 
 // index.cu
 Index *index_build(Ctx *ctx, Genome *const *refs, int32_t nRefs);
@@ -229,7 +239,7 @@ struct MapOutput {
 };
 void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_t nq,
                  bool wantRows, bool wantCgi, MapOutput &out);
-QSketch *qsketch_create(Ctx *ctx, const Genome *const *queries, int32_t nq, const int32_t *queryIds);
+QSketch *qsketch_create(Ctx *ctx, const Genome *const *queries, int32_t nq, const int32_t *queryIds, const Index *hint);
 uint64_t qsketch_export_bytes(const QSketch *qs);
 void qsketch_export(Ctx *ctx, const QSketch *qs, void *devBuf, uint64_t cap);
 QSketch *qsketch_import(Ctx *ctx, const void *devBuf, uint64_t bytes);

@@ -133,10 +133,13 @@ Index *index_build(Ctx *ctx, Genome *const *refs, int32_t nRefs)
   std::vector<int32_t> contigGenome;
   std::vector<uint32_t> binOff(1, 0);
   uint64_t totalPos = 0;
+  std::vector<unsigned long long> bitBase;
+  unsigned long long totalBits = 0;
   for (int g = 0; g < nRefs; g++) {
     const Genome *G = refs[g];
     if (!G) fail(BANI_ERR_ARG, "null genome handle");
     if (G->device != ctx->device) fail(BANI_ERR_ARG, "genome lives on another device");
+    ix->members.emplace(G->uid, (int32_t)desc.size());          // first occurrence wins if a genome is listed twice
     for (int c = 0; c < G->nContigs; c++) {
       SeqDesc d;
       d.packed = G->packed.p + G->wordOff[c];
@@ -147,6 +150,7 @@ Index *index_build(Ctx *ctx, Genome *const *refs, int32_t nRefs)
       desc.push_back(d);
       ix->contigLen.push_back(G->len[c]);
       contigGenome.push_back(g);
+      bitBase.push_back(totalBits); totalBits += ((unsigned long long)G->len[c] + 31) & ~31ull;
       uint64_t bins = (fragLen > 20) ? (uint64_t)G->len[c] / (uint64_t)(fragLen - 20) + 1 : 1;
       if (binOff.back() + bins > 0xfffffff0ull) fail(BANI_ERR_LIMIT, "reference too large for 32-bit position bins");
       binOff.push_back((uint32_t)(binOff.back() + bins));
@@ -178,6 +182,10 @@ Index *index_build(Ctx *ctx, Genome *const *refs, int32_t nRefs)
     return ix.release();
   }
 
+  ix->validBits.alloc((size_t)(totalBits / 32) + 1, st);
+  BANI_CUDA(cudaMemsetAsync(ix->validBits.p, 0, ix->validBits.bytes(), st));
+  ix->contigBitBase.alloc(nC, st);
+  BANI_CUDA(cudaMemcpyAsync(ix->contigBitBase.p, bitBase.data(), 8 * (size_t)nC, cudaMemcpyHostToDevice, st));
   DevBuf<SeqDesc> d_desc(nC, st);
   BANI_CUDA(cudaMemcpyAsync(d_desc.p, desc.data(), sizeof(SeqDesc) * (size_t)nC, cudaMemcpyHostToDevice, st));
 
@@ -191,7 +199,8 @@ Index *index_build(Ctx *ctx, Genome *const *refs, int32_t nRefs)
       if (cap > 0xfffffff0ull) fail(BANI_ERR_LIMIT, "more than 2^32 minimizers in one index shard");
       th.alloc(cap, st); tw.alloc(cap, st); ts.alloc(cap, st);
       Stage sg(ctx, "ref_sketch", (double)ix->totalLen / 4.0);
-      M = sketch_sequences(ctx, d_desc.p, nC, ix->contigLen.data(), 0, th.p, tw.p, ts.p, cap, ix->contigRecOff.p);
+      M = sketch_sequences(ctx, d_desc.p, nC, ix->contigLen.data(), 0, th.p, tw.p, ts.p, cap, ix->contigRecOff.p,
+                           ix->validBits.p, ix->contigBitBase.p);
       sg.bytes((double)ix->totalLen / 4.0 + 12.0 * (double)M);       // packed bases in, 12-byte records out
       if (M <= cap) break;
       cap = M;

@@ -685,6 +685,7 @@ void Ctx::upload_lut(int smaxNeeded)
 struct FragSrc {
   const uint32_t *packed; const uint32_t *excPos; const uint8_t *excByte;
   int32_t nExc, firstFrag, seqBase, query;
+  int32_t idxSeq;                               // contig ordinal inside the hint index (stage A'), else -1
 };
 
 __global__ void frag_table_kernel(const FragSrc *src, int32_t nSrc, int32_t F, int fragLen, SeqDesc *desc, int32_t *fragQuery, int32_t *fragSeqId)
@@ -697,7 +698,68 @@ __global__ void frag_table_kernel(const FragSrc *src, int32_t nSrc, int32_t F, i
   const int i = f - sr.firstFrag;
   SeqDesc d; d.packed = sr.packed; d.excPos = sr.excPos; d.excByte = sr.excByte; d.nExc = sr.nExc;
   d.startBase = i * fragLen; d.len = fragLen; d.seqId = sr.seqBase + i;                     // :173-175
-  desc[f] = d; fragQuery[f] = sr.query; fragSeqId[f] = sr.seqBase + i;
+  if (desc) desc[f] = d;
+  fragQuery[f] = sr.query; fragSeqId[f] = sr.seqBase + i;
+}
+
+// ---- stage A': fragment sketches of a genome the index was built from, WITHOUT hashing it again.
+// The windows of fragment [start, start + fragLen) are exactly the contig windows that lie inside it, and the index
+// holds, per contig, one record for every change of the window minimizer (emitted at position e = wpos + w - 1).  So
+//   Q(fragment) = { hash(r) : e_r in [A, B] }  +  hash(r*) if r* is still the minimizer at some VALID position of [A, B]
+// with A = start + w - 1, B = start + fragLen - k (the fragment's first / last window end) and r* the last record
+// emitted before A: it stays current until the next record is emitted, and the sketch only looks at valid positions
+// (commonFunc.hpp:131), hence the validity bitmap written by the reference sketch launch.  Same multiset up to
+// duplicates as sketching the fragment as a stand-alone sequence (computeMap.hpp:260); sort/unique follows as usual.
+__device__ __forceinline__ bool any_valid_bit(const uint32_t *bits, unsigned long long b0, unsigned long long b1 /* inclusive */)
+{
+  unsigned long long wi = b0 >> 5; const unsigned long long we = b1 >> 5;
+  uint32_t m = 0xFFFFFFFFu << (b0 & 31);
+  for (; wi <= we; wi++, m = 0xFFFFFFFFu) {
+    uint32_t v = __ldg(&bits[wi]) & m;
+    if (wi == we) v &= 0xFFFFFFFFu >> (31 - (b1 & 31));
+    if (v) return true;
+  }
+  return false;
+}
+
+__global__ void frag_ref_range_kernel(const FragSrc *src, int32_t nSrc, int32_t F, int fragLen, int k, int w,
+                                      const int32_t *recWpos, const uint32_t *contigRecOff, const uint32_t *validBits,
+                                      const unsigned long long *bitBase, uint32_t *rFirst, uint32_t *rCnt)
+{
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f > F) return;
+  if (f == F) { rCnt[f] = 0; return; }
+  int lo = 0, hi = nSrc - 1;
+  while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (src[mid].firstFrag <= f) lo = mid; else hi = mid - 1; }
+  const int seq = src[lo].idxSeq;
+  const int start = (f - src[lo].firstFrag) * fragLen;
+  const uint32_t rlo = contigRecOff[seq], rhi = contigRecOff[seq + 1];
+  const int wA = start, wB = start + fragLen - k - w + 1;
+  uint32_t first = rlo, cnt = 0;
+  if (wB >= wA) {
+    uint32_t a = rlo, b = rhi;
+    while (a < b) { const uint32_t m = (a + b) >> 1; if (recWpos[m] < wA) a = m + 1; else b = m; }
+    const uint32_t rA = a;
+    b = rhi;
+    while (a < b) { const uint32_t m = (a + b) >> 1; if (recWpos[m] <= wB) a = m + 1; else b = m; }
+    const uint32_t rB = a;
+    uint32_t inc = 0;
+    if (rA > rlo) {
+      const int A = start + w - 1, B = start + fragLen - k;
+      const int hiPos = rA < rhi ? min(B, recWpos[rA] + w - 2) : B;       // r* is current up to the position before the next emission
+      if (hiPos >= A && any_valid_bit(validBits, bitBase[seq] + (unsigned long long)A, bitBase[seq] + (unsigned long long)hiPos)) inc = 1;
+    }
+    first = rA - inc; cnt = rB - rA + inc;
+  }
+  rFirst[f] = first; rCnt[f] = cnt;
+}
+
+__global__ void frag_ref_gather_kernel(const uint32_t *recHash, const uint32_t *rFirst, const uint32_t *rawStart, int32_t F, uint32_t *raw)
+{
+  const int f = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (f >= F) return;
+  const uint32_t a = rFirst[f], o = rawStart[f], n = rawStart[f + 1] - o;
+  for (uint32_t i = lane; i < n; i += 32) raw[o + i] = recHash[a + i];
 }
 
 // sorted unique hashes of every fragment, back to back (the sort/unique kernel works in place on the raw segments)
@@ -711,11 +773,18 @@ __global__ void compact_sketch_kernel(const uint32_t *raw, const uint32_t *rawSt
 
 static constexpr uint64_t FRAG_MAX = 1u << 17;       // fragments per piece
 
-QSketch *qsketch_create(Ctx *ctx, const Genome *const *queries, int32_t nq, const int32_t *queryIds)
+QSketch *qsketch_create(Ctx *ctx, const Genome *const *queries, int32_t nq, const int32_t *queryIds, const Index *hint)
 {
   cudaStream_t st = ctx->stream;
   const int k = ctx->prm.kmer_size, w = ctx->prm.window_size, fragLen = ctx->prm.frag_len;
   if (fragLen < 1 || fragLen > 60000) fail(BANI_ERR_LIMIT, "fragment length %d outside the supported range [1, 60000]", fragLen);
+  static const bool noReuse = getenv("BANI_NO_SKETCH_REUSE") != nullptr;         // test switch: always hash the queries
+  if (hint && (noReuse || hint->device != ctx->device || hint->M == 0 || !hint->validBits.p)) hint = nullptr;
+  auto member = [&](const Genome *Q) -> int32_t {                                // first contig ordinal inside the hint index
+    if (!hint) return -1;
+    auto it = hint->members.find(Q->uid);
+    return it == hint->members.end() ? -1 : it->second;
+  };
   auto qs = std::make_unique<QSketch>();
   qs->device = ctx->device; qs->k = k; qs->w = w; qs->fragLen = fragLen;
   qs->queryId.resize(nq); qs->totalFragments.assign(nq, 0);
@@ -726,6 +795,7 @@ QSketch *qsketch_create(Ctx *ctx, const Genome *const *queries, int32_t nq, cons
     // ---- fragment sources of this piece (Map::mapQuery, computeMap.hpp:131-189)
     std::vector<FragSrc> src;
     int64_t F64 = 0;
+    bool pieceFromIndex = false;
     int q1 = q0;
     while (q1 < nq) {
       const Genome *Q = queries[q1];
@@ -734,6 +804,9 @@ QSketch *qsketch_create(Ctx *ctx, const Genome *const *queries, int32_t nq, cons
       uint64_t nf = 0;
       for (int c = 0; c < Q->nContigs; c++) { int L = Q->len[c]; if (!(L < w || L < k || L < fragLen)) nf += L / fragLen; }
       if (q1 > q0 && (uint64_t)F64 + nf > FRAG_MAX) break;
+      const int32_t mem = member(Q);
+      if (q1 > q0 && (mem >= 0) != pieceFromIndex) break;           // a piece is either derived from the index or hashed
+      pieceFromIndex = mem >= 0;
       int32_t seqCounter = 0;
       for (int c = 0; c < Q->nContigs; c++) {
         const int L = Q->len[c];
@@ -744,7 +817,7 @@ QSketch *qsketch_create(Ctx *ctx, const Genome *const *queries, int32_t nq, cons
         sr.nExc = (int32_t)(Q->excOff[c + 1] - Q->excOff[c]);
         sr.excPos = sr.nExc ? Q->excPos.p + Q->excOff[c] : nullptr;
         sr.excByte = sr.nExc ? Q->excByte.p + Q->excOff[c] : nullptr;
-        sr.firstFrag = (int32_t)F64; sr.seqBase = seqCounter; sr.query = q1 - q0;
+        sr.firstFrag = (int32_t)F64; sr.seqBase = seqCounter; sr.query = q1 - q0; sr.idxSeq = mem >= 0 ? mem + c : -1;
         src.push_back(sr);
         F64 += fc; seqCounter += fc;
       }
@@ -758,17 +831,39 @@ QSketch *qsketch_create(Ctx *ctx, const Genome *const *queries, int32_t nq, cons
     if (F > 0) {
       BANI_SCRATCH(FragSrc, d_src, src.size());
       BANI_CUDA(cudaMemcpyAsync(d_src.p, src.data(), sizeof(FragSrc) * src.size(), cudaMemcpyHostToDevice, st));
-      BANI_SCRATCH(SeqDesc, d_desc, F);
       pc->fragQuery.alloc(F, st); pc->fragSeqId.alloc(F, st);
+      View<uint32_t> rawHash;
+      BANI_SCRATCH(uint32_t, rawStart, (size_t)F + 1);
+      uint64_t T = 0;
+      if (pieceFromIndex) {
+        // ---- A': the queries of this piece are genomes of the index: read their minimizers from it
+        frag_table_kernel<<<nblk(F), 256, 0, st>>>(d_src.p, (int32_t)src.size(), F, fragLen, nullptr, pc->fragQuery.p, pc->fragSeqId.p);
+        ctx->launches++;
+        Stage sg(ctx, "q_from_index", 0);
+        BANI_SCRATCH(uint32_t, rFirst, (size_t)F + 1);
+        BANI_SCRATCH(uint32_t, rCnt, (size_t)F + 1);
+        frag_ref_range_kernel<<<nblk((uint64_t)F + 1), 256, 0, st>>>(d_src.p, (int32_t)src.size(), F, fragLen, k, w, hint->wpos.p, hint->contigRecOff.p,
+                                                                     hint->validBits.p, hint->contigBitBase.p, rFirst.p, rCnt.p);
+        ctx->launches++;
+        { size_t tb = cub_scan_u32_temp((size_t)F + 1);
+          BANI_SCRATCH(uint8_t, tmp, tb);
+          cub_exclusive_sum_u32(tmp.p, tb, rCnt.p, rawStart.p, (size_t)F + 1, st); }
+        uint32_t t32 = 0;
+        BANI_CUDA(cudaMemcpyAsync(&t32, rawStart.p + F, 4, cudaMemcpyDeviceToHost, st));
+        BANI_CUDA(cudaStreamSynchronize(st));
+        T = t32;
+        rawHash = ctx->view<uint32_t>(BANI_SLOT_ID, std::max<uint64_t>(T, 1));
+        frag_ref_gather_kernel<<<nblk((uint64_t)F * 32), 256, 0, st>>>(hint->hash.p, rFirst.p, rawStart.p, F, rawHash.p);
+        ctx->launches++;
+        sg.bytes(8.0 * (double)T + 16.0 * F);
+      } else {
+      BANI_SCRATCH(SeqDesc, d_desc, F);
       frag_table_kernel<<<nblk(F), 256, 0, st>>>(d_src.p, (int32_t)src.size(), F, fragLen, d_desc.p, pc->fragQuery.p, pc->fragSeqId.p);
       ctx->launches++;
 
       // ---- A: fragment sketches
-      View<uint32_t> rawHash;
-      BANI_SCRATCH(uint32_t, rawStart, (size_t)F + 1);
       uint64_t perFrag = std::max(1, fragLen - k + 1);
       uint64_t cap = std::min<uint64_t>((uint64_t)F * perFrag, (uint64_t)F * (uint64_t)(2.6 * fragLen / (w + 1) + 64));
-      uint64_t T = 0;
       for (int attempt = 0; attempt < 2; attempt++) {
         if (cap > 0xfffffff0ull) fail(BANI_ERR_LIMIT, "query chunk produces more than 2^32 minimizers");
         rawHash = ctx->view<uint32_t>(BANI_SLOT_ID, std::max<uint64_t>(cap, 1));
@@ -777,6 +872,7 @@ QSketch *qsketch_create(Ctx *ctx, const Genome *const *queries, int32_t nq, cons
         sg.bytes((double)F * fragLen / 4.0 + 4.0 * (double)T);
         if (T <= cap) break;
         cap = T;
+      }
       }
 
       // ---- B: sorted unique hashes per fragment, then packed back to back
@@ -904,7 +1000,7 @@ QSketch *qsketch_import(Ctx *ctx, const void *devBuf, uint64_t bytes)
 void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_t nq,
                  bool wantRows, bool wantCgi, MapOutput &out)
 {
-  std::unique_ptr<QSketch> qs(qsketch_create(ctx, queries, nq, nullptr));
+  std::unique_ptr<QSketch> qs(qsketch_create(ctx, queries, nq, nullptr, ix));
   const QSketch *one = qs.get();
   qsketch_map(ctx, ix, &one, 1, wantRows, wantCgi, out);
   out.totalQueryFragments = qs->totalFragments;

@@ -48,6 +48,7 @@ struct SketchArgs {
   uint32_t *o_segStart;
   unsigned long long *tileState;    // nTiles, zero-initialised
   unsigned long long *o_total;
+  uint32_t *o_validBits; const unsigned long long *bitBase;   // optional: validity bitmap of the hashed positions
 };
 
 // ------------------------------------------------------------------ MurmurHash3_x64_128, low 32 bits of h1
@@ -237,6 +238,24 @@ sketch_kernel(const SketchArgs a)
   }
   s_vmask[tid] = (uint16_t)vmask;
   __syncthreads();
+  if (a.o_validBits && he > t0) {
+    // validity of the tile's own positions [t0, he) as aligned 32-bit words (t0 and the bit base are multiples of 32
+    // resp. 16: slot q = p - hs, 16 slots per s_vmask entry)
+    const int d = t0 - hs;                                  // slots of the left halo
+    const int nw = (he - t0 + 31) >> 5;
+    const unsigned long long wbase = (a.bitBase[seq] + (unsigned long long)t0) >> 5;
+    for (int wi = tid; wi < nw; wi += SK_THREADS) {
+      const int q = d + wi * 32;                            // first slot of this word
+      const int e0 = q >> 4, sh = q & 15;
+      unsigned long long bits = 0;
+#pragma unroll
+      for (int e = 0; e < 3; e++) if (e0 + e < SK_THREADS) bits |= (unsigned long long)s_vmask[e0 + e] << (16 * e);
+      uint32_t word = (uint32_t)(bits >> sh);
+      const int rem = he - t0 - wi * 32;
+      if (rem < 32) word &= (1u << rem) - 1u;
+      a.o_validBits[wbase + wi] = word;
+    }
+  }
 
   // ---- phase 3: window minima of the thread's 16 positions (kept in registers)
   uint64_t M[SK_P];
@@ -351,7 +370,7 @@ static void launch_sketch(const SketchArgs &a, cudaStream_t st)
 
 uint64_t sketch_sequences(Ctx *ctx, const SeqDesc *d_desc, int32_t nSeq, const int32_t *h_len, int32_t uniformLen,
                           uint32_t *o_hash, int32_t *o_wpos, int32_t *o_seqId, uint64_t cap,
-                          uint32_t *o_segStart)
+                          uint32_t *o_segStart, uint32_t *o_validBits, const unsigned long long *bitBase)
 {
   cudaStream_t st = ctx->stream;
   const int k = ctx->prm.kmer_size, w = ctx->prm.window_size;
@@ -361,7 +380,7 @@ uint64_t sketch_sequences(Ctx *ctx, const SeqDesc *d_desc, int32_t nSeq, const i
     if (o_segStart) BANI_CUDA(cudaMemsetAsync(o_segStart, 0, 4, st));
     return 0;
   }
-  const int tileLen = (SK_SLOTS - 2 * (w - 1)) & ~15;
+  const int tileLen = (SK_SLOTS - 2 * (w - 1)) & ~31;        // multiple of 32: tiles write whole words of the validity bitmap
   uint64_t tiles = 0;
   int32_t uniformTiles = 0;
   DevBuf<uint32_t> d_tileOff;
@@ -391,6 +410,7 @@ uint64_t sketch_sequences(Ctx *ctx, const SeqDesc *d_desc, int32_t nSeq, const i
   a.k = k; a.w = w; a.tileLen = tileLen;
   a.o_hash = o_hash; a.o_wpos = o_wpos; a.o_seqId = o_seqId; a.cap = cap; a.o_segStart = o_segStart;
   a.tileState = state.p; a.o_total = state.p + tiles;
+  a.o_validBits = o_validBits; a.bitBase = bitBase;
   if (k == 16) launch_sketch<16>(a, st);
   else if (k == 21) launch_sketch<21>(a, st);
   else launch_sketch<0>(a, st);

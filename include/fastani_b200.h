@@ -186,10 +186,14 @@ BANI_API int  bani_map_cgi(bani_ctx *ctx, const bani_index *ix, bani_genome *con
  * set of query genomes.  bani_map_cgi() builds it internally; building it separately lets a multi-GPU run
  * sketch each query ONCE (rank r sketches queries r, r+N, ...), move the sketches between GPUs
  * (export -> NCCL all-gather -> import; a sketch is ~0.33 bytes per query base) and map every sketch against
- * each rank's reference shard.  query_ids[i] is reported as qryGenomeId (NULL: 0..n-1). */
+ * each rank's reference shard.  query_ids[i] is reported as qryGenomeId (NULL: 0..n-1).
+ * hint (optional): an index on the same device.  Queries that are genomes the hint index was built from get their
+ * fragment sketches from its minimizer records instead of being hashed again (the windows of a fragment are the
+ * contig windows inside it) -- all-vs-all runs, and every rank of the multi-GPU split, hash each genome once.
+ * bani_map_genome / bani_map_cgi pass their index as the hint themselves. */
 typedef struct bani_qsketch bani_qsketch;
 BANI_API int  bani_qsketch_create(bani_ctx *ctx, bani_genome *const *queries, int32_t n_queries, const int32_t *query_ids,
-                                  bani_qsketch **out);
+                                  const bani_index *hint, bani_qsketch **out);
 BANI_API void bani_qsketch_destroy(bani_qsketch *qs);
 BANI_API int  bani_qsketch_info(const bani_qsketch *qs, int32_t *n_queries, uint64_t *n_fragments, uint64_t *n_hashes,
                                 uint64_t *export_bytes);

@@ -348,3 +348,47 @@ def test_query_sketch_objects_export_import_and_map():
         fb.QuerySketch.from_device_buffer(ctx, buf.data_ptr(), 32)
     with pytest.raises(fb.BaniError):
         fb.QuerySketch.from_device_buffer(fb.Context(fb.Parameters(kmerSize=21)), buf.data_ptr(), i1["export_bytes"])
+
+
+_REUSE_SCRIPT = r"""
+import hashlib, os, sys
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+import fastani_b200 as fb
+from fastani_b200.synth import synth_genome
+G = os.path.join(sys.argv[1], "tests", "golden")
+edge = fb.read_fasta(os.path.join(G, "edge_mixed.fa"))
+sh = fb.read_fasta(os.path.join(G, "Shigella_flexneri_2a_01.fna.gz"))
+# a genome with palindromic k-mers (invalid positions), N runs and lower case around fragment borders
+rng = np.random.default_rng(5)
+pal = b"ACGTACGTTGCATGCA"                       # its own reverse complement: an invalid position wherever it occurs
+body = synth_genome(9, 1, 0, 0, 40000).tobytes()
+tricky = bytearray(body)
+for pos in (0, 984, 999, 1000, 1016, 1999, 2990, 3000, 8000, 11990, 12000, 20000, 39984):
+    tricky[pos:pos + 16] = pal
+tricky[5000:5400] = b"N" * 400
+tricky[14990:15020] = b"n" * 30
+tricky[25000:25016] = b"A" * 16
+for k, L in ((16, 3000), (16, 1000), (21, 3000), (11, 400)):
+    ctx = fb.Context(fb.Parameters(kmerSize=k, minReadLength=L))
+    gs = ctx.genomes([edge, [("tricky", bytes(tricky))], sh if L == 3000 and k == 16 else [("t2", bytes(tricky[7:]))]])
+    sk = fb.Sketch(ctx, gs)
+    for g in gs:
+        m = fb.Map(ctx, sk, g)
+        print(k, L, len(m.rows), hashlib.sha256(m.rows.tobytes()).hexdigest(), m.totalQueryFragments, m.counters.as_dict()["sum_s"])
+    res, tot, _ = fb.compute_cgi(ctx, sk, gs)
+    print(hashlib.sha256(res.tobytes()).hexdigest())
+"""
+
+
+def test_fragment_sketches_from_the_index_equal_hashed_ones():
+    """Stage A' (fragment sketches read from the index a query genome is a member of) against stage A (the fragment
+    hashed as a stand-alone sequence): same rows and counters on real, edge-case and palindrome/N-laden genomes."""
+    import subprocess, sys
+    from conftest import ROOT
+    outs = []
+    for env in ({}, {"BANI_NO_SKETCH_REUSE": "1"}):
+        r = subprocess.run([sys.executable, "-c", _REUSE_SCRIPT, ROOT], env=dict(os.environ, **env), capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(r.stdout)
+    assert outs[0] == outs[1] and outs[0].count("\n") == 16
