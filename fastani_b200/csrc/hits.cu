@@ -9,7 +9,7 @@
 // device-wide 64-bit sort of (fragment, record) keys and the three passes over it (flags, scan, write) collapse
 // into one kernel that reads each hit once:
 //   1  gather   the position lists of the fragment's s query hashes -> shared memory
-//   2  sort     block-wide radix sort on the significant bits of the record index
+//   2  sort     block-wide radix sort (own: 8-bit digits, warp-match stable ranking) on the significant bits of the record index
 //   3  fetch    (seqId, wpos) of every sorted hit -> shared memory (neighbouring ranks = neighbouring records)
 //   4  L1       hit i opens a raw region iff hit i+minHits-1 is on the same contig less than fragLen ahead
 //               (:324-336); overlapping raw regions merge (:342-350), which is a LOCAL rule on sorted hits:
@@ -21,8 +21,6 @@
 // ones (many near-identical references) stay on the device-wide sort path in map.cu.
 #define BANI_FILE_TAG 1
 #include "common.cuh"
-#include <cub/block/block_radix_sort.cuh>
-#include <cub/block/block_scan.cuh>
 
 namespace bani {
 
@@ -45,103 +43,170 @@ __global__ void frag_classify_kernel(const uint32_t *segStart, const unsigned lo
   if (cls < 5) { const uint32_t o = atomicAdd(&classCount[cls], 1u); if (cls < 4) classList[(size_t)cls * F + o] = (uint32_t)f; }
 }
 
+// Block-wide stable LSD radix sort of CAP = 256 * ITEMS 32-bit keys held in shared memory, 8 bits per pass.
+// Warp w owns the keys [w * 32 * ITEMS, (w+1) * 32 * ITEMS) of the current order and ranks them round by round
+// (32 consecutive keys per round): lanes with the same digit find each other with match.any, the lowest of them
+// bumps the warp's digit counter once for the whole group, the others take their place from the lane order --
+// which keeps equal digits in input order, the property LSD needs.  Then one thread per digit turns the per-warp
+// counts into offsets (prefix over warps, block scan over digits) and the keys are scattered to the other buffer.
+// Returns the buffer that holds the sorted keys.
 template <int ITEMS>
-struct FragL1Smem {
-  static constexpr int CAP = 256 * ITEMS;
-  using Sort = cub::BlockRadixSort<uint32_t, 256, ITEMS>;
-  using Scan = cub::BlockScan<uint32_t, 256>;
-  union U {
-    typename Sort::TempStorage sort;
-    typename Scan::TempStorage scan;
-    int32_t seq[CAP];
-  };
-};
+__device__ __forceinline__ uint32_t *block_radix_sort(uint32_t *in, uint32_t *out, uint16_t *hist /* [8][256] */,
+                                                       uint32_t *digitBase /* [256] */, uint32_t *wsum /* [8] */, int keyBits)
+{
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const uint32_t ltMask = (1u << lane) - 1u;
+  for (int shift = 0; shift < keyBits; shift += 8) {
+    for (int i = tid; i < 8 * 256 / 2; i += 256) reinterpret_cast<uint32_t *>(hist)[i] = 0;
+    __syncthreads();
+    uint32_t key[ITEMS]; uint32_t lr[ITEMS];
+    uint16_t *myHist = hist + w * 256;
+#pragma unroll
+    for (int r = 0; r < ITEMS; r++) {
+      key[r] = in[w * 32 * ITEMS + r * 32 + lane];
+      const uint32_t d = (key[r] >> shift) & 255u;
+      const uint32_t m = __match_any_sync(0xffffffffu, d);
+      const int leader = __ffs(m) - 1;
+      uint32_t old = 0;
+      if (lane == leader) { old = myHist[d]; myHist[d] = (uint16_t)(old + __popc(m)); }
+      old = __shfl_sync(0xffffffffu, old, leader);
+      lr[r] = old + __popc(m & ltMask);
+      __syncwarp();                                   // the counter update must be visible to the next round's leaders
+    }
+    __syncthreads();
+    {
+      // thread = digit: counts of the 8 warps -> exclusive prefix over warps; total -> exclusive scan over digits
+      uint32_t acc = 0;
+#pragma unroll
+      for (int ww = 0; ww < 8; ww++) { const uint32_t c = hist[ww * 256 + tid]; hist[ww * 256 + tid] = (uint16_t)acc; acc += c; }
+      uint32_t incl = acc;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+      if (lane == 31) wsum[w] = incl;
+      __syncthreads();
+      uint32_t base = incl - acc;
+      for (int ww = 0; ww < w; ww++) base += wsum[ww];
+      digitBase[tid] = base;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < ITEMS; r++) {
+      const uint32_t d = (key[r] >> shift) & 255u;
+      out[digitBase[d] + myHist[d] + lr[r]] = key[r];
+    }
+    __syncthreads();
+    uint32_t *t = in; in = out; out = t;
+  }
+  return in;
+}
 
 template <int ITEMS>
 __global__ void __launch_bounds__(256)
 frag_l1_kernel(const FragL1Args a, const uint32_t *list, uint32_t count)
 {
-  using S = FragL1Smem<ITEMS>;
-  constexpr int CAP = S::CAP;
+  constexpr int CAP = 256 * ITEMS;
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  uint32_t *s_key = reinterpret_cast<uint32_t *>(smem_raw);                 // CAP keys, later the wpos of rank r
-  typename S::U &u = *reinterpret_cast<typename S::U *>(smem_raw + sizeof(uint32_t) * CAP);
-  int32_t *s_w = reinterpret_cast<int32_t *>(s_key);
+  uint32_t *bufA = reinterpret_cast<uint32_t *>(smem_raw);                  // CAP
+  uint32_t *bufB = bufA + CAP;                                              // CAP
+  uint16_t *hist = reinterpret_cast<uint16_t *>(bufB + CAP);                // 8 * 256
+  uint32_t *digitBase = reinterpret_cast<uint32_t *>(hist + 8 * 256);       // 256
+  uint32_t *wsum = digitBase + 256;                                         // 8
   if (blockIdx.x >= count) return;
-  const int f = (int)list[blockIdx.x], tid = threadIdx.x;
+  const int f = (int)list[blockIdx.x], tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const uint32_t t0 = a.segStart[f];
   const int s = a.sCount[f];
   const unsigned long long base = a.hitOff[t0];
   const int n = (int)(a.hitOff[a.segStart[f + 1]] - base);
 
-  // ---- 1: gather (one position list per thread; lists are short)
-  for (int q = tid; q < s; q += 256) {
-    const uint32_t lo = a.hitLo[t0 + q], cnt = a.hitCnt[t0 + q];
-    const uint32_t o = (uint32_t)(a.hitOff[t0 + q] - base);
-    for (uint32_t j = 0; j < cnt; j++) s_key[o + j] = __ldg(&a.posIdx[lo + j]);
+  // ---- 1: gather.  Thread per OUTPUT slot: the owning position list is found by a binary search over the lists'
+  //         offsets (staged in shared memory), so all loads of a fragment are independent and neighbouring lanes read
+  //         neighbouring entries of the same few lists.  (Sketches larger than the staging area: thread per list.)
+  if (s <= 256) {
+    uint32_t *m_o = reinterpret_cast<uint32_t *>(hist), *m_lo = m_o + 260;
+    for (int q = tid; q < s; q += 256) { m_o[q] = (uint32_t)(a.hitOff[t0 + q] - base); m_lo[q] = a.hitLo[t0 + q]; }
+    if (tid == 0) m_o[s] = (uint32_t)n;
+    __syncthreads();
+    for (int i = tid; i < n; i += 256) {
+      int lo = 0, hi = s - 1;                     // last list whose offset is <= i
+      while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (m_o[mid] <= (uint32_t)i) lo = mid; else hi = mid - 1; }
+      bufA[i] = __ldg(&a.posIdx[m_lo[lo] + ((uint32_t)i - m_o[lo])]);
+    }
+    __syncthreads();
+  } else {
+    for (int q = tid; q < s; q += 256) {
+      const uint32_t lo = a.hitLo[t0 + q], cnt = a.hitCnt[t0 + q];
+      const uint32_t o = (uint32_t)(a.hitOff[t0 + q] - base);
+      for (uint32_t j = 0; j < cnt; j++) bufA[o + j] = __ldg(&a.posIdx[lo + j]);
+    }
   }
-  for (int i = n + tid; i < CAP; i += 256) s_key[i] = 0xFFFFFFFFu;
+  for (int i = n + tid; i < CAP; i += 256) bufA[i] = 0xFFFFFFFFu;
   __syncthreads();
   // ---- 2: sort by record index
+  const uint32_t *sorted = block_radix_sort<ITEMS>(bufA, bufB, hist, digitBase, wsum, a.keyBits);
+  // ---- 3: (seqId, wpos) of the sorted hits; rank r = i*256 + tid (neighbouring lanes = neighbouring records)
   uint32_t keys[ITEMS];
 #pragma unroll
-  for (int i = 0; i < ITEMS; i++) keys[i] = s_key[tid * ITEMS + i];
+  for (int i = 0; i < ITEMS; i++) keys[i] = sorted[i * 256 + tid];
   __syncthreads();
-  typename S::Sort(u.sort).SortBlockedToStriped(keys, 0, a.keyBits);
-  __syncthreads();
-  // ---- 3: (seqId, wpos) of the sorted hits; rank r = i*256 + tid
+  int32_t *s_w = reinterpret_cast<int32_t *>(bufA), *s_seq = reinterpret_cast<int32_t *>(bufB);
 #pragma unroll
   for (int i = 0; i < ITEMS; i++) {
     const int r = i * 256 + tid;
-    if (r < n) { s_w[r] = __ldg(&a.recWpos[keys[i]]); u.seq[r] = __ldg(&a.recSeq[keys[i]]); }
+    if (r < n) { s_w[r] = __ldg(&a.recWpos[keys[i]]); s_seq[r] = __ldg(&a.recSeq[keys[i]]); }
   }
   __syncthreads();
-  // ---- 4: L1 flags of ranks [tid*ITEMS, +ITEMS)
+  // ---- 4: L1 flags.  Item i of lane `lane` in warp `wid` is rank i*256 + wid*32 + lane: consecutive lanes read
+  //         consecutive words (no bank conflicts), and a ballot gives the head flags of 32 consecutive ranks in order
   const int mh = a.minHits[s];
   auto qual = [&](int i, int32_t &start) -> bool {
     const int rb = i + mh - 1;
     if (rb >= n) return false;
-    if (u.seq[rb] != u.seq[i]) return false;
+    if (s_seq[rb] != s_seq[i]) return false;
     const int32_t wb = s_w[rb];
     if (wb - s_w[i] >= a.fragLen) return false;
     start = max(0, wb - a.fragLen + 1);
     return true;
   };
-  uint32_t headMask = 0, tailMask = 0;
+  uint32_t headMask = 0, tailMask = 0;           // bit i: item i of this thread
+  uint32_t headBallot[ITEMS];                    // heads of the 32 ranks of this warp's slice of item i
   int32_t starts[ITEMS];
+  uint16_t *slice = hist;                        // [ITEMS][8] head counts per (item, warp) = per 32 consecutive ranks
 #pragma unroll
   for (int i = 0; i < ITEMS; i++) {
-    const int r = tid * ITEMS + i;
+    const int r = i * 256 + tid;
     int32_t st = 0;
     starts[i] = 0;
+    bool hd = false;
     if (r < n && qual(r, st)) {
       starts[i] = st;
       int32_t sp, sn;
-      const bool merged = r > 0 && u.seq[r - 1] == u.seq[r] && qual(r - 1, sp) && s_w[r - 1] >= st;
-      const bool nextMerges = r + 1 < n && u.seq[r + 1] == u.seq[r] && qual(r + 1, sn) && s_w[r] >= sn;
-      if (!merged) headMask |= 1u << i;
+      const bool merged = r > 0 && s_seq[r - 1] == s_seq[r] && qual(r - 1, sp) && s_w[r - 1] >= st;
+      const bool nextMerges = r + 1 < n && s_seq[r + 1] == s_seq[r] && qual(r + 1, sn) && s_w[r] >= sn;
+      hd = !merged;
+      if (hd) headMask |= 1u << i;
       if (!nextMerges) tailMask |= 1u << i;
     }
-  }
-  // values needed after the scan reuses the union: read them first
-  int32_t hSeq[ITEMS], tEnd[ITEMS];
-#pragma unroll
-  for (int i = 0; i < ITEMS; i++) {
-    const int r = tid * ITEMS + i;
-    hSeq[i] = ((headMask >> i) & 1u) ? u.seq[r] : 0;
-    tEnd[i] = ((tailMask >> i) & 1u) ? s_w[r] : 0;
+    headBallot[i] = __ballot_sync(0xffffffffu, hd);
+    if (lane == 0) slice[i * 8 + wid] = (uint16_t)__popc(headBallot[i]);
   }
   __syncthreads();
-  // ---- 5: ordinals + staging writes
-  uint32_t excl, total;
-  typename S::Scan(u.scan).ExclusiveSum((uint32_t)__popc(headMask), excl, total);
-  uint32_t ord = excl;
+  // ---- 5: ordinals = exclusive prefix over the (item, warp) slices in rank order + position inside the slice
+  uint32_t total = 0;
+  {
+    // every thread scans the <= 256 slice counts it needs (ITEMS * 8 entries, broadcast reads)
+    uint32_t run = 0;
 #pragma unroll
-  for (int i = 0; i < ITEMS; i++) {
-    const bool hd = (headMask >> i) & 1u, tl = (tailMask >> i) & 1u;
-    if (hd) { a.stSeq[base + ord] = hSeq[i]; a.stStart[base + ord] = starts[i]; }
-    ord += hd ? 1u : 0u;
-    if (tl) a.stEnd[base + ord - 1] = tEnd[i];
+    for (int i = 0; i < ITEMS; i++) {
+      uint32_t before = run;
+#pragma unroll
+      for (int ww = 0; ww < 8; ww++) { const uint32_t c = slice[i * 8 + ww]; if (ww < wid) before += c; run += c; }
+      const uint32_t hb = headBallot[i];
+      const uint32_t upto = before + __popc(hb & ((2u << lane) - 1u));     // heads at ranks <= mine
+      const int r = i * 256 + tid;
+      if ((headMask >> i) & 1u) { a.stSeq[base + upto - 1] = s_seq[r]; a.stStart[base + upto - 1] = starts[i]; }
+      if ((tailMask >> i) & 1u) a.stEnd[base + upto - 1] = s_w[r];
+    }
+    total = run;
   }
   if (tid == 0) a.candCount[f] = total;
 }
@@ -150,8 +215,7 @@ template <int ITEMS>
 static void launch_class(const FragL1Args &a, const uint32_t *list, uint32_t count, cudaStream_t st)
 {
   if (count == 0) return;
-  using S = FragL1Smem<ITEMS>;
-  const size_t shm = sizeof(uint32_t) * S::CAP + sizeof(typename S::U);
+  const size_t shm = sizeof(uint32_t) * 2 * 256 * ITEMS + 2 * 8 * 256 + 4 * 256 + 64;
   static bool attr = false;
   if (!attr) { BANI_CUDA(cudaFuncSetAttribute(frag_l1_kernel<ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm)); attr = true; }
   frag_l1_kernel<ITEMS><<<count, 256, shm, st>>>(a, list, count);

@@ -40,14 +40,19 @@ __global__ void unique_scatter_kernel(const uint32_t *sh, const uint32_t *head, 
   if (i == n - 1) { uint32_t U = scan[i] + head[i]; *o_U = U; }
 }
 
+// Twin links.  Only a few percent of the records share their hash with another record, so the link array is
+// pre-filled with "no twin" (memset 0xFF) and only records that have one are written (a 4-byte scatter).
 __global__ void links_kernel(const uint32_t *sh, const uint32_t *posIdx, uint64_t n, uint32_t *link)
 {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  uint32_t r = posIdx[i], h = sh[i];
+  const uint32_t h = sh[i];
+  const bool hasPrev = i > 0 && sh[i - 1] == h, hasNext = i + 1 < n && sh[i + 1] == h;
+  if (!hasPrev && !hasNext) return;
+  const uint32_t r = posIdx[i];
   uint32_t pd = 0xFFFFu, nd = 0xFFFFu;
-  if (i > 0 && sh[i - 1] == h) pd = min(r - posIdx[i - 1], 0xFFFFu);       // stable sort: twins ascend by record index
-  if (i + 1 < n && sh[i + 1] == h) nd = min(posIdx[i + 1] - r, 0xFFFFu);
+  if (hasPrev) pd = min(r - posIdx[i - 1], 0xFFFFu);       // stable sort: twins ascend by record index
+  if (hasNext) nd = min(posIdx[i + 1] - r, 0xFFFFu);
   link[r] = (pd << 16) | nd;
 }
 
@@ -256,6 +261,7 @@ Index *index_build(Ctx *ctx, Genome *const *refs, int32_t nRefs)
   unique_scatter_kernel<<<nblk(M), 256, 0, st>>>(sortedHash.p, head.p, scan.p, M, ix->ukeys.p, ix->uoff.p, d_U.p);
   ctx->launches++;
   { uint32_t Mu = (uint32_t)M; BANI_CUDA(cudaMemcpyAsync(ix->uoff.p + U, &Mu, 4, cudaMemcpyHostToDevice, st)); }
+  BANI_CUDA(cudaMemsetAsync(ix->link.p, 0xFF, 4 * (size_t)M, st));
   links_kernel<<<nblk(M), 256, 0, st>>>(sortedHash.p, ix->posIdx.p, M, ix->link.p);
   ctx->launches++;
   int bits = 8; while (bits < 24 && (1ull << bits) < U) bits++;
