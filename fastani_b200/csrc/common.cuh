@@ -248,6 +248,11 @@ void qsketch_map(Ctx *ctx, const Index *ix, const QSketch *const *sketches, int3
 
 // hits.cu : per-fragment gather + shared-memory sort + L1 candidate regions
 static constexpr unsigned long long FRAG_L1_MAX = 8192;   // hits per fragment handled inside one CTA
+static constexpr int FRAG_NCLASS = 13;                    // size classes: 256 * {1,2,3,4,5,6,7,8,10,12,16,24,32} hits
+__host__ __device__ inline int frag_class_items(int cls)
+{
+  return cls < 8 ? cls + 1 : (cls == 8 ? 10 : cls == 9 ? 12 : cls == 10 ? 16 : cls == 11 ? 24 : 32);
+}
 struct FragL1Args {
   const uint32_t *segStart; const int32_t *sCount; int32_t F;
   const uint32_t *hitLo, *hitCnt; const unsigned long long *hitOff;
@@ -258,7 +263,7 @@ struct FragL1Args {
 };
 void frag_classify(Ctx *ctx, const uint32_t *segStart, const unsigned long long *hitOff, int32_t F,
                    uint32_t *candCount, uint32_t *fragClass, uint32_t *classCount, uint32_t *classList, unsigned long long maxFast);
-void frag_l1_fast(Ctx *ctx, const FragL1Args &a, const uint32_t *classList, const uint32_t classCount[4]);
+void frag_l1_fast(Ctx *ctx, const FragL1Args &a, const uint32_t *classList, const uint32_t *classCount);
 void cand_stage(Ctx *ctx, const int32_t *cFrag, const int32_t *cSeq, const int32_t *cStart, const int32_t *cEnd, uint32_t C,
                 const uint32_t *segStart, const unsigned long long *hitOff, int32_t *stSeq, int32_t *stStart, int32_t *stEnd,
                 uint32_t *candCount);

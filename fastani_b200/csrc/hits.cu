@@ -17,7 +17,7 @@
 //               i+1 qualifies and starts at or before i's position
 //   5  emit     block scan of head flags -> candidate ordinals; {seqId, start, end} written to a staging
 //               area addressed by the fragment's global hit offset (a fragment never has more regions than hits)
-// Fragments are binned by hit count into four size classes (1024 / 2048 / 4096 / 8192 hits per CTA); larger
+// Fragments are binned by hit count into 13 size classes (256 ... 8192 hits per CTA, frag_class_items); larger
 // ones (many near-identical references) stay on the device-wide sort path in map.cu.
 #define BANI_FILE_TAG 1
 #include "common.cuh"
@@ -33,14 +33,11 @@ __global__ void frag_classify_kernel(const uint32_t *segStart, const unsigned lo
   if (f >= F) return;
   const unsigned long long n = hitOff[segStart[f + 1]] - hitOff[segStart[f]];
   candCount[f] = 0;
-  uint32_t cls = 5;                                    // no hits
-  if (n > maxFast) cls = 4;                        // device-wide path
-  else if (n > 4096) cls = 3;
-  else if (n > 2048) cls = 2;
-  else if (n > 1024) cls = 1;
-  else if (n > 0) cls = 0;
+  uint32_t cls = FRAG_NCLASS + 1;                      // no hits
+  if (n > maxFast) cls = FRAG_NCLASS;                  // device-wide path
+  else if (n > 0) { cls = 0; while (n > 256ull * (unsigned long long)frag_class_items(cls)) cls++; }
   fragClass[f] = cls;
-  if (cls < 5) { const uint32_t o = atomicAdd(&classCount[cls], 1u); if (cls < 4) classList[(size_t)cls * F + o] = (uint32_t)f; }
+  if (cls <= FRAG_NCLASS) { const uint32_t o = atomicAdd(&classCount[cls], 1u); if (cls < FRAG_NCLASS) classList[(size_t)cls * F + o] = (uint32_t)f; }
 }
 
 // Block-wide stable LSD radix sort of CAP = 256 * ITEMS 32-bit keys held in shared memory, 8 bits per pass.
@@ -225,20 +222,31 @@ void frag_classify(Ctx *ctx, const uint32_t *segStart, const unsigned long long 
                    uint32_t *candCount, uint32_t *fragClass, uint32_t *classCount /* 8, zeroed here */, uint32_t *classList /* 4*F */,
                    unsigned long long maxFast)
 {
-  BANI_CUDA(cudaMemsetAsync(classCount, 0, 8 * sizeof(uint32_t), ctx->stream));
+  BANI_CUDA(cudaMemsetAsync(classCount, 0, (FRAG_NCLASS + 2) * sizeof(uint32_t), ctx->stream));
   frag_classify_kernel<<<nblk(F), 256, 0, ctx->stream>>>(segStart, hitOff, F, candCount, fragClass, classCount, classList, maxFast);
   ctx->launches++;
 }
 
-void frag_l1_fast(Ctx *ctx, const FragL1Args &a, const uint32_t *classList, const uint32_t classCount[4])
+void frag_l1_fast(Ctx *ctx, const FragL1Args &a, const uint32_t *classList, const uint32_t *classCount)
 {
   cudaStream_t st = ctx->stream;
   const size_t F = (size_t)a.F;
-  launch_class<4>(a, classList + 0 * F, classCount[0], st);
-  launch_class<8>(a, classList + 1 * F, classCount[1], st);
-  launch_class<16>(a, classList + 2 * F, classCount[2], st);
-  launch_class<32>(a, classList + 3 * F, classCount[3], st);
-  for (int i = 0; i < 4; i++) if (classCount[i]) ctx->launches++;
+  // one instantiation per size class (frag_class_items): the sort works on 256 * ITEMS slots, so narrow classes
+  // keep the padding of a fragment's hit list small
+  launch_class<1>(a, classList + 0 * F, classCount[0], st);
+  launch_class<2>(a, classList + 1 * F, classCount[1], st);
+  launch_class<3>(a, classList + 2 * F, classCount[2], st);
+  launch_class<4>(a, classList + 3 * F, classCount[3], st);
+  launch_class<5>(a, classList + 4 * F, classCount[4], st);
+  launch_class<6>(a, classList + 5 * F, classCount[5], st);
+  launch_class<7>(a, classList + 6 * F, classCount[6], st);
+  launch_class<8>(a, classList + 7 * F, classCount[7], st);
+  launch_class<10>(a, classList + 8 * F, classCount[8], st);
+  launch_class<12>(a, classList + 9 * F, classCount[9], st);
+  launch_class<16>(a, classList + 10 * F, classCount[10], st);
+  launch_class<24>(a, classList + 11 * F, classCount[11], st);
+  launch_class<32>(a, classList + 12 * F, classCount[12], st);
+  for (int i = 0; i < FRAG_NCLASS; i++) if (classCount[i]) ctx->launches++;
   BANI_CUDA(cudaGetLastError());
 }
 

@@ -126,7 +126,7 @@ __global__ void mask_hits_kernel(const uint32_t *segStart, int32_t F, uint32_t T
 {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t > T) return;
-  bigCnt[t] = (t < T && fragClass[seg_of(segStart, F, t)] == 4u) ? hitCnt[t] : 0u;
+  bigCnt[t] = (t < T && fragClass[seg_of(segStart, F, t)] == (uint32_t)FRAG_NCLASS) ? hitCnt[t] : 0u;
 }
 
 // ------------------------------------------------------------------ E: L1 candidate regions (device-wide path)
@@ -771,7 +771,7 @@ __global__ void compact_sketch_kernel(const uint32_t *raw, const uint32_t *rawSt
   for (uint32_t i = lane; i < n; i += 32) out[o + i] = raw[a + i];
 }
 
-static constexpr uint64_t FRAG_MAX = 1u << 17;       // fragments per piece
+static constexpr uint64_t FRAG_MAX = 1u << 19;       // fragments per piece
 
 QSketch *qsketch_create(Ctx *ctx, const Genome *const *queries, int32_t nq, const int32_t *queryIds, const Index *hint)
 {
@@ -1079,14 +1079,14 @@ void qsketch_map(Ctx *ctx, const Index *ix, const QSketch *const *sketches, int3
           BANI_SCRATCH(uint32_t, candCount, (size_t)F + 1);
           BANI_SCRATCH(uint32_t, candOff, (size_t)F + 1);
           BANI_SCRATCH(uint32_t, fragClass, F);
-          BANI_SCRATCH(uint32_t, classList, (size_t)4 * F);
-          BANI_SCRATCH(uint32_t, classCount, 8);
+          BANI_SCRATCH(uint32_t, classList, (size_t)FRAG_NCLASS * F);
+          BANI_SCRATCH(uint32_t, classCount, FRAG_NCLASS + 2);
           BANI_SCRATCH(int32_t, stSeq, N);
           BANI_SCRATCH(int32_t, stStart, N);
           BANI_SCRATCH(int32_t, stEnd, N);
           static const long long maxFast = [] { const char *e = getenv("BANI_FRAG_L1_MAX"); long long v = e ? atoll(e) : (long long)FRAG_L1_MAX;
                                                 return std::max(0ll, std::min(v, (long long)FRAG_L1_MAX)); }();
-          uint32_t hClass[8];
+          uint32_t hClass[FRAG_NCLASS + 2];
           { Stage sg(ctx, "frag_l1", 12.0 * N);                // 4 B list entry + 8 B (seqId, wpos) per hit
             frag_classify(ctx, segStart.p, hitOff.p, F, candCount.p, fragClass.p, classCount.p, classList.p, (unsigned long long)maxFast);
             BANI_CUDA(cudaMemcpyAsync(hClass, classCount.p, sizeof hClass, cudaMemcpyDeviceToHost, st));
@@ -1096,7 +1096,7 @@ void qsketch_map(Ctx *ctx, const Index *ix, const QSketch *const *sketches, int3
             fa.keyBits = 1; while (fa.keyBits < 32 && (1ull << fa.keyBits) < ix->M) fa.keyBits++;
             fa.stSeq = stSeq.p; fa.stStart = stStart.p; fa.stEnd = stEnd.p; fa.candCount = candCount.p;
             frag_l1_fast(ctx, fa, classList.p, hClass); }
-          if (hClass[4] > 0) {
+          if (hClass[FRAG_NCLASS] > 0) {
             // ---- device-wide path for the oversized fragments: (fragment, record) keys, one radix sort, flags + scan + write
             BANI_SCRATCH(uint32_t, bigCnt, T + 1);
             BANI_SCRATCH(unsigned long long, bigOff, T + 1);

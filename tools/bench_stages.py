@@ -22,11 +22,12 @@ for it in range(reps):
     ctx.profile(True); ctx.profile_read()
     t = time.time()
     sk = fb.Sketch(ctx, gs)
+    ctx.sync(); t1 = time.time()
     res, tot, ctr = fb.compute_cgi(ctx, sk, gs)
     ctx.sync()
     dt = time.time() - t
     prof = ctx.profile_read()
     sk.close()
-print("step %.1f ms  pairs/s %.0f  counters %s" % (dt * 1e3, nG * nG / dt, ctr.as_dict()))
+print("step %.1f ms (index %.1f + map %.1f)  pairs/s %.0f  counters %s" % (dt * 1e3, (t1 - t) * 1e3, (dt - (t1 - t)) * 1e3, nG * nG / dt, ctr.as_dict()))
 for k, v in prof.items():
     print("  %-16s %9.2f ms  x%d" % (k, v[0], v[2]))
