@@ -41,7 +41,7 @@ __global__ void unique_scatter_kernel(const uint32_t *sh, const uint32_t *head, 
 }
 
 // Twin links.  Only a few percent of the records share their hash with another record, so the link array is
-// pre-filled with "no twin" (memset 0xFF) and only records that have one are written (a 4-byte scatter).
+// pre-filled with "no twin" (memset 0xFF) and only records that have a NEAR one are written (a 4-byte scatter).
 __global__ void links_kernel(const uint32_t *sh, const uint32_t *posIdx, uint64_t n, uint32_t *link)
 {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -53,7 +53,9 @@ __global__ void links_kernel(const uint32_t *sh, const uint32_t *posIdx, uint64_
   uint32_t pd = 0xFFFFu, nd = 0xFFFFu;
   if (hasPrev) pd = min(r - posIdx[i - 1], 0xFFFFu);       // stable sort: twins ascend by record index
   if (hasNext) nd = min(posIdx[i + 1] - r, 0xFFFFu);
-  link[r] = (pd << 16) | nd;
+  // a twin 65535 or more records away reads as "no twin" (no window is that long): in collections of related
+  // genomes almost every hash recurs in a sister genome millions of records away, and none of those needs a write
+  if (pd != 0xFFFFu || nd != 0xFFFFu) link[r] = (pd << 16) | nd;
 }
 
 // dir[b] = number of unique keys whose top dirBits are < b, b = 0 .. 2^dirBits
@@ -264,7 +266,7 @@ Index *index_build(Ctx *ctx, Genome *const *refs, int32_t nRefs)
   BANI_CUDA(cudaMemsetAsync(ix->link.p, 0xFF, 4 * (size_t)M, st));
   links_kernel<<<nblk(M), 256, 0, st>>>(sortedHash.p, ix->posIdx.p, M, ix->link.p);
   ctx->launches++;
-  int bits = 8; while (bits < 24 && (1ull << bits) < U) bits++;
+  int bits = 8; while (bits < 24 && (1ull << bits) < U) bits++;       // <= 64 MB: the directory stays L2-resident during a lookup launch
   ix->dirBits = bits;
   ix->dir.alloc((1u << bits) + 1, st);
   dir_fill_kernel<<<nblk((1ull << bits) + 1), 256, 0, st>>>(ix->ukeys.p, (uint32_t)U, bits, ix->dir.p);

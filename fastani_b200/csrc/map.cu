@@ -309,7 +309,8 @@ struct L2PArgs {
   const uint4 *rec; const uint32_t *contigRecOff;
   int fragLen, cmw, sLimit, shiftA;
   uint32_t *cB0, *cE0, *cLast, *cNEv, *cChunks;   // per candidate
-  const uint32_t *cOff;                            // stream offset in 32-byte units (16 events)
+  const uint32_t *cOff;                            // first 32-byte slot of the candidate's stream; step k is slot cOff + 32 * k
+  const unsigned long long *grpOff;                // per warp group of 32 sorted candidates: first step row
   uint16_t *events;
   const uint32_t *perm; uint32_t warpBytes;
   int32_t *cPos, *cBest; unsigned long long *ctr_n2;
@@ -369,6 +370,22 @@ __global__ void l2_sortkey_kernel(const uint32_t *cNEv, uint32_t C, uint32_t *ke
   val[c] = c;
 }
 
+// steps of a warp group = steps of its longest member = the first in sorted order
+__global__ void l2_group_steps_kernel(const uint32_t *cChunks, const uint32_t *perm, uint32_t C, uint32_t nGrp, uint32_t *grpSteps)
+{
+  const uint32_t G = blockIdx.x * blockDim.x + threadIdx.x;
+  if (G > nGrp) return;
+  grpSteps[G] = G < nGrp ? cChunks[perm[G * 32]] : 0u;
+}
+__global__ void l2_stream_base_kernel(const uint32_t *perm, const unsigned long long *grpOff, uint32_t C, uint32_t *cOff)
+{
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= C) return;
+  cOff[perm[g]] = (uint32_t)(grpOff[g >> 5] * 32ull + (g & 31u));
+}
+// event e of a stream that starts at 32-byte slot `base`: 16 events per slot, consecutive steps 32 slots apart
+__device__ __forceinline__ size_t ev_index(uint32_t base, uint32_t e) { return ((size_t)base + (size_t)(e >> 4) * 32) * 16 + (e & 15u); }
+
 static constexpr int L2E_THREADS = 256;
 static constexpr int L2E_BUCKETS = 4096;         // directory over h >> shiftA (clamped): ~s*w/2^(32-shiftA) <= 1 query hash per bucket near 0
 
@@ -423,8 +440,9 @@ l2_events_kernel(const L2PArgs a)
     const uint32_t nEv = a.cNEv[c];
     if (nEv == 0) continue;
     const uint32_t b0 = a.cB0[c], nInit = a.cE0[c] - b0, nAll = a.cLast[c] - b0;
-    uint16_t *ev = a.events + (size_t)a.cOff[c] * 16;
-    if (lane < ((16u - (nEv & 15u)) & 15u)) ev[nEv + lane] = (uint16_t)nop;    // pad the last 32-byte step
+    const uint32_t sb = a.cOff[c];
+    uint16_t *ev = a.events;
+    if (lane < ((16u - (nEv & 15u)) & 15u)) ev[ev_index(sb, nEv + lane)] = (uint16_t)nop;    // pad the last 32-byte step
     const uint4 *rp = a.rec + b0;
     uint32_t rb = lane;
     uint4 nxt = make_uint4(0, 0, 0, 0);
@@ -447,11 +465,11 @@ l2_events_kernel(const L2PArgs a)
       const uint32_t mb = min(back, rb);
       const bool isNew = can && pd > mb;
       const bool sc = (rb + 1 >= nInit) && (rb + 1 != nAll);
-      ev[rb2 - mb] = (uint16_t)((isNew ? (code | EV_D) : nop) | (sc ? EV_S : 0u));
+      ev[ev_index(sb, rb2 - mb)] = (uint16_t)((isNew ? (code | EV_D) : nop) | (sc ? EV_S : 0u));
       // r LEAVES
       if (rb + fwd < nAll) {
         const bool gone = can && nd >= fwd;
-        ev[rb2 + fwd] = (uint16_t)((gone ? code : nop) | ((rc.y >> 31) ? 0u : EV_S));
+        ev[ev_index(sb, rb2 + fwd)] = (uint16_t)((gone ? code : nop) | ((rc.y >> 31) ? 0u : EV_S));
       }
     }
   }
@@ -476,7 +494,9 @@ l2_seq_kernel(const L2PArgs a)
 
   uint32_t c = 0, nEv = 0; int s = 1;
   if (gid < a.C) { c = a.perm[gid]; nEv = a.cNEv[c]; s = a.sCount[a.cFrag[c]]; }
-  const uint4 *strm = reinterpret_cast<const uint4 *>(a.events) + (nEv ? (size_t)a.cOff[c] * 2 : (size_t)0);
+  // this lane's 32-byte slot of step k: row (grpOff[warp] + k) of 32 slots, column = lane (== cOff[c] + 32 * k)
+  const unsigned long long row0 = (gid >> 5) < ((a.C + 31u) >> 5) ? a.grpOff[gid >> 5] : 0ull;
+  const uint4 *strm = reinterpret_cast<const uint4 *>(a.events) + ((size_t)row0 * 32 + (size_t)lane) * 2;
   const uint32_t nSt = (nEv + 15) >> 4;                                  // 32-byte steps of this lane
   uint32_t maxSt = nSt;
   for (int o = 16; o; o >>= 1) maxSt = max(maxSt, __shfl_xor_sync(0xffffffffu, maxSt, o));
@@ -492,11 +512,11 @@ l2_seq_kernel(const L2PArgs a)
   // each lane streams its own events: 32 bytes (one DRAM sector) per step, loaded two steps ahead
   uint4 n1a = nop4, n1b = nop4, n2a = nop4, n2b = nop4;
   if (nSt > 0) { n1a = __ldg(strm); n1b = __ldg(strm + 1); }
-  if (nSt > 1) { n2a = __ldg(strm + 2); n2b = __ldg(strm + 3); }
+  if (nSt > 1) { n2a = __ldg(strm + 64); n2b = __ldg(strm + 65); }
   for (uint32_t stp = 0; stp < maxSt; stp++) {
     const uint4 ca = n1a, cb = n1b;
     n1a = n2a; n1b = n2b; n2a = nop4; n2b = nop4;
-    if (stp + 2 < nSt) { n2a = __ldg(strm + 2 * (stp + 2)); n2b = __ldg(strm + 2 * (stp + 2) + 1); }
+    if (stp + 2 < nSt) { n2a = __ldg(strm + 64 * (size_t)(stp + 2)); n2b = __ldg(strm + 64 * (size_t)(stp + 2) + 1); }
     const uint32_t wv[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
     const uint32_t kb = stp * 16;
 #pragma unroll
@@ -1193,20 +1213,7 @@ void qsketch_map(Ctx *ctx, const Index *ix, const QSketch *const *sketches, int3
               lp.cPos = cPos.p; lp.cBest = cBest.p; lp.ctr_n2 = d_n2.p; lp.events = nullptr; lp.perm = nullptr;
               l2_bounds_kernel<<<nblk((uint64_t)C + 1), 256, 0, st>>>(lp); ctx->launches++;
               if (lp.sLimit > 0) {
-                { size_t tb = cub_scan_u64_temp((size_t)C + 1);
-                  BANI_SCRATCH(uint8_t, tmp, tb);
-                  BANI_SCRATCH(unsigned long long, cOff64, (size_t)C + 1);
-                  cub_exclusive_sum_u32_to_u64(tmp.p, tb, cChunks.p, (uint64_t *)cOff64.p, (size_t)C + 1, st);
-                  unsigned long long totalChunks = 0;
-                  BANI_CUDA(cudaMemcpyAsync(&totalChunks, cOff64.p + C, 8, cudaMemcpyDeviceToHost, st));
-                  BANI_CUDA(cudaStreamSynchronize(st));
-                  totalSteps = totalChunks;
-                  if (totalChunks > 0xfffffff0ull) fail(BANI_ERR_LIMIT, "query chunk schedules more than 2^36 window events");
-                  tb = cub_scan_u32_temp((size_t)C + 1);
-                  BANI_SCRATCH(uint8_t, tmp2, tb);
-                  cub_exclusive_sum_u32(tmp2.p, tb, cChunks.p, cOff.p, (size_t)C + 1, st);
-                  BANI_SCRATCH(uint16_t, events, (size_t)totalChunks * 16 + 64);
-                  lp.events = events.p; }
+                // candidates by descending event count: rank g -> warp g / 32, lane g % 32 of the sequential kernel
                 BANI_SCRATCH(uint32_t, skey, C);
                 BANI_SCRATCH(uint32_t, skey2, C);
                 BANI_SCRATCH(uint32_t, sval, C);
@@ -1216,6 +1223,23 @@ void qsketch_map(Ctx *ctx, const Index *ix, const QSketch *const *sketches, int3
                   BANI_SCRATCH(uint8_t, tmp, tb);
                   cub_sort_pairs_u32(tmp.p, tb, skey.p, skey2.p, sval.p, perm.p, C, 20, st); }
                 lp.perm = perm.p;
+                // event streams, interleaved per warp: step k of lane l of warp G is the 32-byte slot (grpOff[G] + k) * 32 + l,
+                // so a warp reads 1 KB contiguous per step while every 32-byte sector still belongs to one candidate
+                const uint32_t nGrp = (C + 31) / 32;
+                BANI_SCRATCH(uint32_t, grpSteps, (size_t)nGrp + 1);
+                BANI_SCRATCH(unsigned long long, grpOff, (size_t)nGrp + 1);
+                l2_group_steps_kernel<<<nblk((uint64_t)nGrp + 1), 256, 0, st>>>(cChunks.p, perm.p, C, nGrp, grpSteps.p); ctx->launches++;
+                { size_t tb = cub_scan_u64_temp((size_t)nGrp + 1);
+                  BANI_SCRATCH(uint8_t, tmp, tb);
+                  cub_exclusive_sum_u32_to_u64(tmp.p, tb, grpSteps.p, (uint64_t *)grpOff.p, (size_t)nGrp + 1, st); }
+                unsigned long long totalGrpSteps = 0;
+                BANI_CUDA(cudaMemcpyAsync(&totalGrpSteps, grpOff.p + nGrp, 8, cudaMemcpyDeviceToHost, st));
+                BANI_CUDA(cudaStreamSynchronize(st));
+                totalSteps = totalGrpSteps * 32;                      // 32-byte slots
+                if (totalSteps > 0xfffffff0ull) fail(BANI_ERR_LIMIT, "query chunk schedules more than 2^36 window events");
+                BANI_SCRATCH(uint16_t, events, (size_t)totalSteps * 16 + 64);
+                lp.events = events.p; lp.grpOff = grpOff.p;
+                l2_stream_base_kernel<<<nblk(C), 256, 0, st>>>(perm.p, grpOff.p, C, cOff.p); ctx->launches++;
                 static bool attrSet = false;
                 const size_t shmE = 4 * ((size_t)lp.sLimit + 4) + 4 * (L2E_BUCKETS + 4);
                 const size_t shmS = (size_t)L2S_WARPS * lp.warpBytes;
