@@ -307,7 +307,7 @@ struct L2PArgs {
   const uint32_t *fragCandOff;
   const uint32_t *fragHash; const uint32_t *segStart; const int32_t *sCount;
   const uint4 *rec; const uint32_t *contigRecOff;
-  int fragLen, cmw, sLimit, shiftA;
+  int fragLen, cmw, sLimit, shiftA, nBuckets;      // nBuckets: 1024 or 4096 (power of two), directory over h >> shiftA
   uint32_t *cB0, *cE0, *cLast, *cNEv, *cChunks;   // per candidate
   const uint32_t *cOff;                            // first 32-byte slot of the candidate's stream; step k is slot cOff + 32 * k
   const unsigned long long *grpOff;                // per warp group of 32 sorted candidates: first step row
@@ -387,7 +387,8 @@ __global__ void l2_stream_base_kernel(const uint32_t *perm, const unsigned long 
 __device__ __forceinline__ size_t ev_index(uint32_t base, uint32_t e) { return ((size_t)base + (size_t)(e >> 4) * 32) * 16 + (e & 15u); }
 
 static constexpr int L2E_THREADS = 256;
-static constexpr int L2E_BUCKETS = 4096;         // directory over h >> shiftA (clamped): ~s*w/2^(32-shiftA) <= 1 query hash per bucket near 0
+static constexpr int L2E_BUCKETS = 4096;         // largest directory over h >> shiftA (clamped): ~1 query hash per bucket near 0;
+                                                 // shards that see few candidates per fragment use 1024 (cheaper to build)
 
 // Event schedule of one candidate in closed form.  With rb = r - b0, nInit = e0 - b0, nAll = last - b0 and the
 // per-record window links of the index (back, fwd, tie; index.cu):
@@ -414,15 +415,17 @@ l2_events_kernel(const L2PArgs a)
   {
     const uint32_t *Qg = a.fragHash + a.segStart[f];
     for (int i = tid; i < s + 3; i += L2E_THREADS) Q[i] = i < s ? Qg[i] : 0xFFFFFFFFu;
-    for (int i = tid; i <= L2E_BUCKETS; i += L2E_THREADS) tab[i] = 0;
+    const int NB = a.nBuckets;
+    for (int i = tid; i <= NB; i += L2E_THREADS) tab[i] = 0;
     __syncthreads();
-    for (int i = tid; i < s; i += L2E_THREADS) atomicAdd(&tab[min(Q[i] >> a.shiftA, (uint32_t)(L2E_BUCKETS - 1))], 1u);
+    for (int i = tid; i < s; i += L2E_THREADS) atomicAdd(&tab[min(Q[i] >> a.shiftA, (uint32_t)(NB - 1))], 1u);
     __syncthreads();
-    // exclusive prefix over the bucket counts: 16 consecutive buckets per thread
-    constexpr int PER = L2E_BUCKETS / L2E_THREADS;
-    uint32_t cnt[PER], sum = 0;
+    // exclusive prefix over the bucket counts: NB / 256 consecutive buckets per thread
+    constexpr int PERMAX = L2E_BUCKETS / L2E_THREADS;
+    const int PER = NB / L2E_THREADS;
+    uint32_t cnt[PERMAX], sum = 0;
 #pragma unroll
-    for (int i = 0; i < PER; i++) { cnt[i] = tab[tid * PER + i]; sum += cnt[i]; }
+    for (int i = 0; i < PERMAX; i++) { cnt[i] = i < PER ? tab[tid * PER + i] : 0u; sum += cnt[i]; }
     uint32_t incl = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
@@ -431,8 +434,8 @@ l2_events_kernel(const L2PArgs a)
     uint32_t run = incl - sum;
     for (int i = 0; i < wid; i++) run += s_wsum[i];
 #pragma unroll
-    for (int i = 0; i < PER; i++) { tab[tid * PER + i] = run; run += cnt[i]; }
-    if (tid == L2E_THREADS - 1) tab[L2E_BUCKETS] = run;
+    for (int i = 0; i < PERMAX; i++) if (i < PER) { tab[tid * PER + i] = run; run += cnt[i]; }
+    if (tid == L2E_THREADS - 1) tab[NB] = run;
     __syncthreads();
   }
   const uint32_t nop = ev_rank((uint32_t)s) | EV_M | EV_D;
@@ -452,7 +455,7 @@ l2_events_kernel(const L2PArgs a)
       if (rb + 32 < nAll) nxt = __ldg(rp + rb + 32);
       const uint32_t h = rc.x;
       // rank of h in Q: directory, then two probes (the sentinels and the sorted order make them unconditional)
-      uint32_t j = tab[min(h >> a.shiftA, (uint32_t)(L2E_BUCKETS - 1))];
+      uint32_t j = tab[min(h >> a.shiftA, (uint32_t)(a.nBuckets - 1))];
       const uint32_t q0 = Q[j], q1 = Q[j + 1];
       bool match = (q0 == h) || (q1 == h);
       j += (q0 < h) + (q1 < h);
@@ -1201,7 +1204,10 @@ void qsketch_map(Ctx *ctx, const Index *ix, const QSketch *const *sketches, int3
               // fast path: needs the window links of the index (cmw >= 2) and ranks that fit the event code
               lp.sLimit = (cmw >= 2 && ix->cmw == cmw) ? std::min(smax, L2_SMAX) : 0;
               // bucket width near 0 ~ 2^32 / (s * w): minimizer hashes are minima of w hashes, density w/2^32 at 0
-              { int sh = 20; while (sh > 8 && ((uint64_t)std::max(smax, 1) * (uint64_t)w << sh) > (1ull << 32)) sh--; lp.shiftA = sh; }
+              lp.nBuckets = ((uint64_t)C >= 8ull * (uint64_t)F) ? L2E_BUCKETS : 1024;      // few candidates per fragment: building a big directory is not worth it
+              { static const int forced = [] { const char *e = getenv("BANI_L2E_BUCKETS"); return e ? atoi(e) : 0; }();      // test switch
+                if (forced == 1024 || forced == L2E_BUCKETS) lp.nBuckets = forced; }
+              { int sh = lp.nBuckets == L2E_BUCKETS ? 20 : 22; while (sh > 8 && ((uint64_t)std::max(smax, 1) * (uint64_t)w << sh) > ((1ull << 32) * (uint64_t)(L2E_BUCKETS / lp.nBuckets))) sh--; lp.shiftA = sh; }
               lp.warpBytes = (uint32_t)(std::max(lp.sLimit, 1) + 1) * 32u;      // one state byte per rank 0..s and lane
               BANI_SCRATCH(uint32_t, cB0, C);          // (one scratch slot per source line)
               BANI_SCRATCH(uint32_t, cE0, C);
