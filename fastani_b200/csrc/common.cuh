@@ -117,6 +117,7 @@ struct QPiece {
   DevBuf<int32_t>  sCount;           // F  : s
   DevBuf<int32_t>  fragQuery;        // F  : query slot inside the piece (0 .. nq)
   DevBuf<int32_t>  fragSeqId;        // F  : querySeqId of the mapping records (fragment ordinal inside its genome)
+  std::vector<int32_t> qFragOff;     // nq+1 (host): first fragment of every query of the piece
 };
 struct QSketch {
   int device = 0; int k = 0, w = 0, fragLen = 0;

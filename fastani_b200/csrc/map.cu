@@ -28,6 +28,7 @@
 #include "common.cuh"
 #include <algorithm>
 #include <cstring>
+#include <deque>
 
 namespace bani {
 
@@ -817,6 +818,7 @@ QSketch *qsketch_create(Ctx *ctx, const Genome *const *queries, int32_t nq, cons
   while (q0 < nq) {
     // ---- fragment sources of this piece (Map::mapQuery, computeMap.hpp:131-189)
     std::vector<FragSrc> src;
+    std::vector<int32_t> qFragOff;
     int64_t F64 = 0;
     bool pieceFromIndex = false;
     int q1 = q0;
@@ -830,6 +832,7 @@ QSketch *qsketch_create(Ctx *ctx, const Genome *const *queries, int32_t nq, cons
       const int32_t mem = member(Q);
       if (q1 > q0 && (mem >= 0) != pieceFromIndex) break;           // a piece is either derived from the index or hashed
       pieceFromIndex = mem >= 0;
+      qFragOff.push_back((int32_t)F64);
       int32_t seqCounter = 0;
       for (int c = 0; c < Q->nContigs; c++) {
         const int L = Q->len[c];
@@ -850,6 +853,7 @@ QSketch *qsketch_create(Ctx *ctx, const Genome *const *queries, int32_t nq, cons
     if (F64 > 0x7ffffff0ll) fail(BANI_ERR_LIMIT, "a query genome has more than 2^31 fragments");
     auto pc = std::make_unique<QPiece>();
     pc->q0 = q0; pc->nq = q1 - q0; pc->F = (int32_t)F64;
+    qFragOff.push_back((int32_t)F64); pc->qFragOff = qFragOff;
     const int32_t F = pc->F;
     if (F > 0) {
       BANI_SCRATCH(FragSrc, d_src, src.size());
@@ -932,7 +936,7 @@ QSketch *qsketch_create(Ctx *ctx, const Genome *const *queries, int32_t nq, cons
 
 // ---- export / import: one flat DEVICE buffer, so that a query sketch can travel between GPUs (NCCL all-gather)
 //   [u64 x 8: magic, nPieces, nQueries, k, w, fragLen, totalBytes, 0]
-//   [nQueries x {i32 queryId, i32 pad, u64 totalFragments}]   [nPieces x u64 x 6: F, T, smax, q0, nq, 0]
+//   [nQueries x {i32 queryId, i32 firstFragmentInItsPiece, u64 totalFragments}]   [nPieces x u64 x 6: F, T, smax, q0, nq, 0]
 //   per piece, each array padded to 16 bytes: segStart[F+1] sCount[F] fragQuery[F] fragSeqId[F] fragHash[T]
 static inline uint64_t pad16(uint64_t b) { return (b + 15) & ~15ull; }
 static constexpr uint64_t QS_MAGIC = 0x42414e4951534b31ull;
@@ -959,6 +963,8 @@ void qsketch_export(Ctx *ctx, const QSketch *qs, void *devBuf, uint64_t cap)
     int32_t *e = (int32_t *)(h.data() + 64 + 16 * i);
     e[0] = qs->queryId[i]; *(uint64_t *)(e + 2) = qs->totalFragments[i];
   }
+  for (const auto &pc : qs->pieces)
+    for (int q = 0; q < pc->nq; q++) ((int32_t *)(h.data() + 64 + 16 * (uint64_t)(pc->q0 + q)))[1] = pc->qFragOff[q];
   uint64_t *ph = (uint64_t *)(h.data() + 64 + pad16(16 * nQ));
   for (uint64_t i = 0; i < nP; i++) {
     const QPiece &pc = *qs->pieces[i];
@@ -1004,6 +1010,9 @@ QSketch *qsketch_import(Ctx *ctx, const void *devBuf, uint64_t bytes)
   for (uint64_t i = 0; i < nP; i++) {
     auto pc = std::make_unique<QPiece>();
     pc->F = (int32_t)ph[6 * i]; pc->T = ph[6 * i + 1]; pc->smax = (int)ph[6 * i + 2]; pc->q0 = (int)ph[6 * i + 3]; pc->nq = (int)ph[6 * i + 4];
+    if (pc->q0 < 0 || pc->nq < 0 || (uint64_t)pc->q0 + (uint64_t)pc->nq > nQ) fail(BANI_ERR_ARG, "corrupt query sketch buffer");
+    for (int q = 0; q < pc->nq; q++) pc->qFragOff.push_back(((const int32_t *)(h.data() + 64 + 16 * (uint64_t)(pc->q0 + q)))[1]);
+    pc->qFragOff.push_back(pc->F);
     if (pc->F > 0) {
       auto get = [&](void *p, uint64_t b) { if (o + b > bytes) fail(BANI_ERR_ARG, "query sketch buffer truncated");
                                              BANI_CUDA(cudaMemcpyAsync(p, d + o, b, cudaMemcpyDeviceToDevice, st)); o += pad16(b); };
@@ -1017,6 +1026,40 @@ QSketch *qsketch_import(Ctx *ctx, const void *devBuf, uint64_t bytes)
   }
   BANI_CUDA(cudaStreamSynchronize(st));
   return qs.release();
+}
+
+// ---- a sub-range of whole queries of a piece as a piece of its own (offsets rebased); used when a piece gathers
+//      more index hits than one pass should hold (many near-identical references)
+__global__ void rebase_u32_kernel(const uint32_t *in, uint32_t delta, uint64_t n, uint32_t *out)
+{
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i] - delta;
+}
+
+static std::unique_ptr<QPiece> slice_piece(Ctx *ctx, const QPiece &pc, int qa, int qb)
+{
+  cudaStream_t st = ctx->stream;
+  auto sl = std::make_unique<QPiece>();
+  const int32_t fA = pc.qFragOff[qa], fB = pc.qFragOff[qb];
+  sl->q0 = pc.q0 + qa; sl->nq = qb - qa; sl->F = fB - fA; sl->smax = pc.smax;
+  for (int q = qa; q <= qb; q++) sl->qFragOff.push_back(pc.qFragOff[q] - fA);
+  if (sl->F > 0) {
+    uint32_t tA = 0, tB = 0;
+    BANI_CUDA(cudaMemcpyAsync(&tA, pc.segStart.p + fA, 4, cudaMemcpyDeviceToHost, st));
+    BANI_CUDA(cudaMemcpyAsync(&tB, pc.segStart.p + fB, 4, cudaMemcpyDeviceToHost, st));
+    BANI_CUDA(cudaStreamSynchronize(st));
+    sl->T = tB - tA;
+    const size_t F = (size_t)sl->F;
+    sl->segStart.alloc(F + 1, st); sl->sCount.alloc(F, st); sl->fragQuery.alloc(F, st); sl->fragSeqId.alloc(F, st);
+    sl->fragHash.alloc(std::max<uint64_t>(sl->T, 1), st);
+    rebase_u32_kernel<<<nblk(F + 1), 256, 0, st>>>(pc.segStart.p + fA, tA, F + 1, sl->segStart.p);
+    rebase_u32_kernel<<<nblk(F), 256, 0, st>>>((const uint32_t *)pc.fragQuery.p + fA, (uint32_t)qa, F, (uint32_t *)sl->fragQuery.p);
+    ctx->launches += 2;
+    BANI_CUDA(cudaMemcpyAsync(sl->sCount.p, pc.sCount.p + fA, 4 * F, cudaMemcpyDeviceToDevice, st));
+    BANI_CUDA(cudaMemcpyAsync(sl->fragSeqId.p, pc.fragSeqId.p + fA, 4 * F, cudaMemcpyDeviceToDevice, st));
+    if (sl->T) BANI_CUDA(cudaMemcpyAsync(sl->fragHash.p, pc.fragHash.p + tA, 4 * sl->T, cudaMemcpyDeviceToDevice, st));
+  }
+  return sl;
 }
 
 // ------------------------------------------------------------------ host orchestration of stages C..H
@@ -1057,13 +1100,19 @@ void qsketch_map(Ctx *ctx, const Index *ix, const QSketch *const *sketches, int3
    if (!qs) fail(BANI_ERR_ARG, "null query sketch");
    if (qs->device != ctx->device) fail(BANI_ERR_ARG, "query sketch lives on another device");
    if (qs->k != k || qs->w != w || qs->fragLen != fragLen) fail(BANI_ERR_ARG, "query sketch was built with other parameters");
-   for (const auto &pcp : qs->pieces) {
-    const QPiece &pc = *pcp;
+   static const unsigned long long maxHits = [] { const char *e = getenv("BANI_MAX_HITS_PER_PIECE");          // test switch
+                                                 return e ? (unsigned long long)atoll(e) : (3ull << 29); }();           // 1.6 G hits per pass
+   std::deque<const QPiece *> work;
+   std::vector<std::unique_ptr<QPiece>> slices;
+   for (const auto &pcp : qs->pieces) work.push_back(pcp.get());
+   while (!work.empty()) {
+    const QPiece &pc = *work.front();
+    work.pop_front();
     const int nQc = pc.nq, q0 = pc.q0;
     const int32_t F = pc.F;
     const uint64_t T = pc.T;
     const int smax = pc.smax;
-    out.ctr.fragments += F;
+    bool split = false;
     View<uint32_t> fragHash; fragHash.p = pc.fragHash.p; fragHash.n = T;
     View<uint32_t> segStart; segStart.p = pc.segStart.p; segStart.n = (size_t)F + 1;
     View<int32_t> sCount; sCount.p = pc.sCount.p; sCount.n = F;
@@ -1075,7 +1124,6 @@ void qsketch_map(Ctx *ctx, const Index *ix, const QSketch *const *sketches, int3
 
     if (F > 0 && ix->M > 0) {
       ctx->upload_lut(smax);
-      out.ctr.sum_s += T;
 
       if (T > 0 && smax > 0) {
         // ---- C: lookup
@@ -1092,10 +1140,18 @@ void qsketch_map(Ctx *ctx, const Index *ix, const QSketch *const *sketches, int3
         unsigned long long N = 0;
         BANI_CUDA(cudaMemcpyAsync(&N, hitOff.p + T, 8, cudaMemcpyDeviceToHost, st));
         BANI_CUDA(cudaStreamSynchronize(st));
-        out.ctr.hits += N;
-        if (N > 0xfffffff0ull) fail(BANI_ERR_LIMIT, "query chunk gathers more than 2^32 index hits");
+        if (N > maxHits && nQc > 1) {
+          // too many hits for one pass: halve the piece at a query boundary (by fragments) and do the halves instead
+          int qm = 1;
+          while (qm < nQc - 1 && pc.qFragOff[qm] < F / 2) qm++;
+          slices.push_back(slice_piece(ctx, pc, qm, nQc)); work.push_front(slices.back().get());
+          slices.push_back(slice_piece(ctx, pc, 0, qm)); work.push_front(slices.back().get());
+          split = true;
+        }
+        if (!split && N > 0xfffffff0ull) fail(BANI_ERR_LIMIT, "one query genome gathers more than 2^32 index hits");
+        if (!split) out.ctr.hits += N;
 
-        if (N > 0) {
+        if (N > 0 && !split) {
           // ---- D+E: hits -> L1 candidate regions.  Fragments with at most FRAG_L1_MAX hits are handled by
           //      one CTA each (hits.cu); the others go through the device-wide sort below.  Both write their
           //      regions to a staging area addressed by the fragment's hit offset; a scan + copy makes them dense.
@@ -1330,7 +1386,8 @@ void qsketch_map(Ctx *ctx, const Index *ix, const QSketch *const *sketches, int3
       BANI_CUDA(cudaGetLastError());
       BANI_CUDA(cudaStreamSynchronize(st));
     }
-    if (wantCgi) {
+    if (!split) { out.ctr.fragments += F; out.ctr.sum_s += (F > 0 && ix->M > 0) ? T : 0; }
+    if (wantCgi && !split) {
       for (int q = 0; q < nQc; q++)
         for (int g = 0; g < nG; g++) {
           const int32_t cnt = hCount[(size_t)q * nG + g];

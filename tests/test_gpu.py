@@ -387,8 +387,8 @@ def test_fragment_sketches_from_the_index_equal_hashed_ones():
     import subprocess, sys
     from conftest import ROOT
     outs = []
-    for env in ({}, {"BANI_NO_SKETCH_REUSE": "1"}):
+    for env in ({}, {"BANI_NO_SKETCH_REUSE": "1"}, {"BANI_MAX_HITS_PER_PIECE": "500"}):      # the last one forces pieces to be split by queries
         r = subprocess.run([sys.executable, "-c", _REUSE_SCRIPT, ROOT], env=dict(os.environ, **env), capture_output=True, text=True, timeout=900)
         assert r.returncode == 0, r.stderr[-2000:]
         outs.append(r.stdout)
-    assert outs[0] == outs[1] and outs[0].count("\n") == 16
+    assert outs[0] == outs[1] == outs[2] and outs[0].count("\n") == 16
