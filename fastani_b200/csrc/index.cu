@@ -58,18 +58,6 @@ __global__ void links_kernel(const uint32_t *sh, const uint32_t *posIdx, uint64_
   if (pd != 0xFFFFu || nd != 0xFFFFu) link[r] = (pd << 16) | nd;
 }
 
-// dir[b] = number of unique keys whose top dirBits are < b, b = 0 .. 2^dirBits
-__global__ void dir_kernel(const uint32_t *ukeys, uint32_t U, int dirBits, uint32_t *dir)
-{
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= U) return;
-  const int sh = 32 - dirBits;
-  uint32_t bc = ukeys[i] >> sh;
-  long long bp = (i == 0) ? -1 : (long long)(ukeys[i - 1] >> sh);
-  for (long long b = bp + 1; b <= (long long)bc; b++) dir[b] = i;
-  if (i == U - 1) for (uint32_t b = bc + 1; b <= (1u << dirBits); b++) dir[b] = U;
-}
-
 // One 16-byte record per minimizer for the L2 stream: x = hash, y = wpos | tie << 31, z = twin link,
 // w = back | fwd << 16.  back / fwd / tie describe the L2 super-window geometry of computeL2MappedRegions
 // (computeMap.hpp:418-497) around this record, which does not depend on the candidate (cmw is fixed):

@@ -6,21 +6,26 @@
 // (src/cgi/include/computeCoreIdentity.hpp:166-298).
 //
 // The reference maps one fragment at a time.  Here a batch of query genomes is cut into
-// fragments and every stage runs over ALL fragments (or all hits / all candidates) of the batch:
+// fragments and every stage runs over ALL fragments (or all hits / all candidates) of a piece
+// (<= 2^19 fragments of whole query genomes):
 //
+//   --- query sketch (QSketch: can be built once, exported, moved between GPUs; qsketch_create) ---
 //   A  sketch      fragment minimizers, fragment-local windows (computeMap.hpp:260)      sketch.cu
-//   B  sort/unique per fragment: sorted unique hashes Q, s = |Q| (computeMap.hpp:268-276)
+//   A' from index  for queries that are genomes of the index: the same multiset read from the
+//                  index's contig-level records + validity bitmap, no second hashing
+//   B  sort/unique per fragment: sorted unique hashes Q, s = |Q| (computeMap.hpp:268-276), packed
+//   --- map phase (qsketch_map) ---
 //   C  lookup      Q -> bucket directory -> unique keys -> position lists (:283-299)
-//   D  hits        gathered as (fragment << 32 | record index) and radix-sorted: the record index
-//                  is monotone in (seqId, wpos), so this is the sort of :320 for all fragments
-//   E  L1          candidate regions: the scan + merge of :322-352 is a LOCAL rule on the sorted
-//                  hits (a hit starts a region unless its left neighbour qualifies and overlaps),
-//                  so regions come from head flags + one prefix sum, in reference order
+//   D+E hits, L1   per fragment in one CTA (hits.cu): gather, sort by record index (monotone in
+//                  (seqId, wpos), i.e. the sort of :320), candidate regions of :322-352 as a LOCAL
+//                  rule on the sorted hits (a hit starts a region unless its left neighbour
+//                  qualifies and overlaps); oversized fragments: device-wide sort path below
 //   F  L2          per candidate: sliding super-window over the position-ordered records with
 //                  the winnowed-MinHash intersection of slidingMap.hpp restated in rank space:
 //                      t* = max{ t : t + #(distinct window hashes not in Q, below q_t) <= s }
 //                      shared = #(q_j present in the window, j <= t*)
-//                  maintained incrementally (each event moves t* by at most one)
+//                  as a parallel pre-pass (bounds, closed-form event schedule) + a lean sequential
+//                  sweep (each event moves t* by at most one)
 //   G  report      identity / upper bound from the (s, shared) table, filter >= cutoff (:375-384),
 //                  rows in (fragment, candidate) order == callback order of reportL2Mappings
 //   H  CGI         1-way best per (fragment, genome); 2-way best per (ref contig, position bin) via
