@@ -129,6 +129,19 @@ int main(int argc, char **argv)
       return 0;
     } catch (const std::exception &e) { std::cerr << "ERROR, " << e.what() << std::endl; return 1; }
   }
+  if (argc == 3 && std::string(argv[1]) == "--selftestWriters") {   // test hook for the writers (no GPU needed): a fixed result set
+    Parameters p;
+    p.querySequences = {"q/a.fa", "q/b.fa", "r/c.fa"}; p.refSequences = {"r/c.fa", "q/a.fa", "r/d.fa"};
+    p.minReadLength = 3000; p.minFraction = 0.2f; p.matrixOutput = true;
+    std::unordered_map<std::string, uint64_t> len = {{"q/a.fa", 150000}, {"q/b.fa", 90000}, {"r/c.fa", 150000}, {"r/d.fa", 3000000}};
+    std::vector<cgi::CGI_Results> v = {
+      {0, 0, 40, 50, 97.75071f}, {1, 0, 50, 50, 100.0f}, {2, 0, 9, 50, 81.5f},          // a -> c, a -> a (self), a -> d (fails minFraction: 27000 < 30000)
+      {0, 1, 20, 30, 88.123456f}, {2, 1, 6, 30, 80.0f},                                  // b -> c, b -> d (18000 >= 18000 passes)
+      {1, 2, 45, 50, 97.5f}, {0, 2, 50, 50, 100.0f}};                                    // c -> a (averaged with a -> c in the matrix), c -> c (self)
+    cgi::outputCGI(p, len, v, argv[2]);
+    cgi::outputPhylip(p, len, v, argv[2]);
+    return 0;
+  }
   Parameters parameters;
   parseandSave(argc, argv, parameters);
   const std::string fileName = parameters.outFileName;

@@ -155,3 +155,27 @@ def test_cli_fails_loudly_without_gpu(tmp_path):
     assert r.returncode == 1 and "no CUDA device" in r.stderr
     r = subprocess.run([_cli(), "-q", f], capture_output=True, text=True)
     assert r.returncode == 1 and "Provide reference file" in r.stderr
+
+
+def test_cli_writers_format(tmp_path):
+    """cgi::outputCGI / outputPhylip of the C++ host (computeCoreIdentity.hpp:307-448) on a fixed result set: row order
+    (query ascending, identity descending), float formatting (%g / %f), the minFraction filter with its float compare,
+    the lower-triangular matrix with both directions averaged and self pairs ignored."""
+    import subprocess
+    out = tmp_path / "w.txt"
+    r = subprocess.run([_cli(), "--selftestWriters", str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(out).read().splitlines() == [
+        "q/a.fa\tq/a.fa\t100\t50\t50", "q/a.fa\tr/c.fa\t97.7507\t40\t50",
+        "q/b.fa\tr/c.fa\t88.1235\t20\t30", "q/b.fa\tr/d.fa\t80\t6\t30",
+        "r/c.fa\tr/c.fa\t100\t50\t50", "r/c.fa\tq/a.fa\t97.5\t45\t50"]
+    avg = "%f" % ((np.float32(97.75071) + np.float32(97.5)) / np.float32(2))
+    assert open(str(out) + ".matrix").read().splitlines() == [
+        "4", "q/a.fa", "q/b.fa\tNA", "r/c.fa\t%s\t%s" % (avg, "%f" % np.float32(88.123456)), "r/d.fa\tNA\t%s\tNA" % ("%f" % np.float32(80.0))]
+    # the same rows through the Python report module
+    lens = {"q/a.fa": 150000, "q/b.fa": 90000, "r/c.fa": 150000, "r/d.fa": 3000000}
+    q, rr = ["q/a.fa", "q/b.fa", "r/c.fa"], ["r/c.fa", "q/a.fa", "r/d.fa"]
+    rows = [(0, 0, 40, 50, 97.75071), (0, 1, 50, 50, 100.0), (0, 2, 9, 50, 81.5), (1, 0, 20, 30, 88.123456), (1, 2, 6, 30, 80.0),
+            (2, 1, 45, 50, 97.5), (2, 0, 50, 50, 100.0)]
+    py = report.output_lines(rows, q, rr, [lens[x] for x in q], [lens[x] for x in rr], 3000, 0.2)
+    assert sorted(py) == sorted(open(out).read().splitlines())
