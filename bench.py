@@ -43,7 +43,7 @@ def parse_args():
     ap.add_argument("--genome-len", type=int, default=5_000_000)
     ap.add_argument("--seed", type=int, default=3)
     ap.add_argument("--ref-sample-refs", type=int, default=0, help="reference arm: references in the bounded sample (0 = one per host core)")
-    ap.add_argument("--ref-sample-queries", type=int, default=2, help="reference arm: queries in the bounded sample")
+    ap.add_argument("--ref-sample-queries", type=int, default=4, help="reference arm: queries in the bounded sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
