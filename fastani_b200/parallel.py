@@ -64,12 +64,15 @@ def gather_tables(cnt_local, idn_local, n_refs, world, rank, dist=None, device=N
     return merge_shards(tables, n_queries, n_refs, world)
 
 
-def exchange_query_sketches(ctx, mine, world, rank, dist, device):
+def exchange_query_sketches(ctx, mine, world, rank, dist, device, importer=None):
     """All-gather of the ranks' QuerySketch objects: each is packed into a flat device buffer (bani_qsketch_export),
     the buffers travel in one padded NCCL all-gather, and the peers' sketches are rebuilt on this device
-    (bani_qsketch_import).  Returns the `world` sketches in rank order (this rank's own object included)."""
+    (bani_qsketch_import).  Returns the `world` sketches in rank order (this rank's own object included).
+    `importer(ctx, ptr, nbytes)` defaults to QuerySketch.from_device_buffer (the CPU/gloo test passes a stand-in)."""
     import torch
-    from .api import QuerySketch
+    if importer is None:
+        from .api import QuerySketch
+        importer = QuerySketch.from_device_buffer
     nbytes = mine.info()["export_bytes"]
     sizes = torch.zeros(world, dtype=torch.int64, device=device)
     sizes[rank] = nbytes
@@ -80,8 +83,9 @@ def exchange_query_sketches(ctx, mine, world, rank, dist, device):
     mine.export_to(send.data_ptr(), width)              # synchronises the library's stream: the bytes are in place
     recv = torch.empty(world * width, dtype=torch.uint8, device=device)
     dist.all_gather_into_tensor(recv, send)
-    torch.cuda.synchronize(device)
+    if getattr(device, "type", str(device)) != "cpu":
+        torch.cuda.synchronize(device)
     out = []
     for r in range(world):
-        out.append(mine if r == rank else QuerySketch.from_device_buffer(ctx, recv.data_ptr() + r * width, sizes[r]))
+        out.append(mine if r == rank else importer(ctx, recv.data_ptr() + r * width, sizes[r]))
     return out

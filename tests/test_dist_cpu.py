@@ -1,6 +1,6 @@
 """CPU, world_size 2 over gloo: the N>1 host path (shard references round-robin, every shard maps all
 queries, gather the dense per-pair tables) gives the single-shard answer.  The per-shard compute here is
-the oracle (no GPU in this container); on the GPU box tests/test_gpu_parallel.py runs the same merge
+the oracle (no GPU in this container); on the GPU box tests/test_gpu.py (shard invariance, query sketch objects) runs the same merge
 with the CUDA path."""
 import os
 import subprocess
@@ -58,3 +58,56 @@ def test_two_shards_gather_equals_single_shard(tmp_path):
                        capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "DIST_OK" in r.stdout
+
+
+EXCHANGE_WORKER = r'''
+import ctypes, os, sys
+import numpy as np
+import torch, torch.distributed as dist
+sys.path.insert(0, os.environ["ROOT"])
+from fastani_b200 import parallel
+
+class FakeSketch:
+    """Stands in for fastani_b200.QuerySketch: same info()/export_to() surface over a host byte string."""
+    def __init__(self, payload): self.payload = payload
+    def info(self): return {"export_bytes": len(self.payload)}
+    def export_to(self, ptr, cap):
+        assert cap >= len(self.payload)
+        ctypes.memmove(ptr, self.payload, len(self.payload))
+
+def importer(ctx, ptr, nbytes):
+    return FakeSketch(ctypes.string_at(ptr, nbytes))
+
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+rng = np.random.default_rng(100 + rank)
+mine = FakeSketch(rng.integers(0, 256, 1000 + 4097 * rank, dtype=np.uint8).tobytes())        # ragged sizes
+got = parallel.exchange_query_sketches(None, mine, world, rank, dist, torch.device("cpu"), importer=importer)
+assert len(got) == world and got[rank] is mine
+for r in range(world):
+    want = np.random.default_rng(100 + r).integers(0, 256, 1000 + 4097 * r, dtype=np.uint8).tobytes()
+    assert got[r].payload == want, (rank, r)
+# the query split of the bench: rank r owns queries r, r+N, ...; together they cover every query once
+nq = 11
+owned = torch.zeros(nq, dtype=torch.int64)
+owned[list(range(rank, nq, world))] = 1
+dist.all_reduce(owned)
+assert owned.tolist() == [1] * nq
+if rank == 0: print("EXCHANGE_OK")
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+def test_query_sketch_exchange_logic_over_gloo(tmp_path):
+    """parallel.exchange_query_sketches (sizes all-reduce, padded all-gather, per-rank slices) with world_size 2 and 3
+    on CPU; the sketch objects are stand-ins, the GPU round trip of real ones is tests/test_gpu.py::test_query_sketch_*."""
+    script = tmp_path / "xworker.py"
+    script.write_text(EXCHANGE_WORKER)
+    env = dict(os.environ, ROOT=ROOT, OMP_NUM_THREADS="1")
+    for n, port in ((2, "29618"), (3, "29619")):
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
+                            "--master-addr", "127.0.0.1", "--master-port", port, str(script)],
+                           capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+        assert "EXCHANGE_OK" in r.stdout
