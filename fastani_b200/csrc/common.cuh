@@ -181,6 +181,10 @@ struct Ctx {
   // Grow-only scratch slots for the per-chunk working set of the mapping pipeline (hit keys, flags,
   // candidate arrays ...): after the first chunk nothing is allocated or freed inside the timed path.
   std::map<int, DevBuf<uint8_t>> slots;
+  // kernel function attributes (dynamic shared memory limit, carve-out) are per DEVICE: remember per context what has
+  // been set, so that a process driving several GPUs (the C++ CLI: one thread + context per GPU) sets them on each
+  std::map<const void *, bool> attrDone;
+  bool first_time(const void *key) { bool &d = attrDone[key]; const bool f = !d; d = true; return f; }
   template <typename T> View<T> view(int id, size_t n)
   {
     DevBuf<uint8_t> &b = slots[id];

@@ -209,12 +209,12 @@ frag_l1_kernel(const FragL1Args a, const uint32_t *list, uint32_t count)
 }
 
 template <int ITEMS>
-static void launch_class(const FragL1Args &a, const uint32_t *list, uint32_t count, cudaStream_t st)
+static void launch_class(Ctx *ctx, const FragL1Args &a, const uint32_t *list, uint32_t count, cudaStream_t st)
 {
   if (count == 0) return;
   const size_t shm = sizeof(uint32_t) * 2 * 256 * ITEMS + 2 * 8 * 256 + 4 * 256 + 64;
-  static bool attr = false;
-  if (!attr) { BANI_CUDA(cudaFuncSetAttribute(frag_l1_kernel<ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm)); attr = true; }
+  if (ctx->first_time((const void *)frag_l1_kernel<ITEMS>))
+    BANI_CUDA(cudaFuncSetAttribute(frag_l1_kernel<ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
   frag_l1_kernel<ITEMS><<<count, 256, shm, st>>>(a, list, count);
 }
 
@@ -233,19 +233,19 @@ void frag_l1_fast(Ctx *ctx, const FragL1Args &a, const uint32_t *classList, cons
   const size_t F = (size_t)a.F;
   // one instantiation per size class (frag_class_items): the sort works on 256 * ITEMS slots, so narrow classes
   // keep the padding of a fragment's hit list small
-  launch_class<1>(a, classList + 0 * F, classCount[0], st);
-  launch_class<2>(a, classList + 1 * F, classCount[1], st);
-  launch_class<3>(a, classList + 2 * F, classCount[2], st);
-  launch_class<4>(a, classList + 3 * F, classCount[3], st);
-  launch_class<5>(a, classList + 4 * F, classCount[4], st);
-  launch_class<6>(a, classList + 5 * F, classCount[5], st);
-  launch_class<7>(a, classList + 6 * F, classCount[6], st);
-  launch_class<8>(a, classList + 7 * F, classCount[7], st);
-  launch_class<10>(a, classList + 8 * F, classCount[8], st);
-  launch_class<12>(a, classList + 9 * F, classCount[9], st);
-  launch_class<16>(a, classList + 10 * F, classCount[10], st);
-  launch_class<24>(a, classList + 11 * F, classCount[11], st);
-  launch_class<32>(a, classList + 12 * F, classCount[12], st);
+  launch_class<1>(ctx, a, classList + 0 * F, classCount[0], st);
+  launch_class<2>(ctx, a, classList + 1 * F, classCount[1], st);
+  launch_class<3>(ctx, a, classList + 2 * F, classCount[2], st);
+  launch_class<4>(ctx, a, classList + 3 * F, classCount[3], st);
+  launch_class<5>(ctx, a, classList + 4 * F, classCount[4], st);
+  launch_class<6>(ctx, a, classList + 5 * F, classCount[5], st);
+  launch_class<7>(ctx, a, classList + 6 * F, classCount[6], st);
+  launch_class<8>(ctx, a, classList + 7 * F, classCount[7], st);
+  launch_class<10>(ctx, a, classList + 8 * F, classCount[8], st);
+  launch_class<12>(ctx, a, classList + 9 * F, classCount[9], st);
+  launch_class<16>(ctx, a, classList + 10 * F, classCount[10], st);
+  launch_class<24>(ctx, a, classList + 11 * F, classCount[11], st);
+  launch_class<32>(ctx, a, classList + 12 * F, classCount[12], st);
   for (int i = 0; i < FRAG_NCLASS; i++) if (classCount[i]) ctx->launches++;
   BANI_CUDA(cudaGetLastError());
 }

@@ -1307,15 +1307,13 @@ void qsketch_map(Ctx *ctx, const Index *ix, const QSketch *const *sketches, int3
                 BANI_SCRATCH(uint16_t, events, (size_t)totalSteps * 16 + 64);
                 lp.events = events.p; lp.grpOff = grpOff.p;
                 l2_stream_base_kernel<<<nblk(C), 256, 0, st>>>(perm.p, grpOff.p, C, cOff.p); ctx->launches++;
-                static bool attrSet = false;
                 const size_t shmE = 4 * ((size_t)lp.sLimit + 4) + 4 * (L2E_BUCKETS + 4);
                 const size_t shmS = (size_t)L2S_WARPS * lp.warpBytes;
                 if (shmE > 200 * 1024 || shmS > 200 * 1024) fail(BANI_ERR_INTERNAL, "L2 shared-memory budget exceeded");
-                if (!attrSet) {
+                if (ctx->first_time((const void *)l2_seq_kernel)) {
                   BANI_CUDA(cudaFuncSetAttribute(l2_events_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
                   BANI_CUDA(cudaFuncSetAttribute(l2_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
                   BANI_CUDA(cudaFuncSetAttribute(l2_seq_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-                  attrSet = true;
                 }
                 sgb.stop();
                 { Stage sg(ctx, "l2_events"); idEv = sg.id(); evBytes = 32.0 * (double)totalSteps;
