@@ -312,7 +312,7 @@ struct L2PArgs {
   const int32_t *cFrag, *cSeq, *cStart, *cEnd; uint32_t C;
   const uint32_t *fragCandOff;
   const uint32_t *fragHash; const uint32_t *segStart; const int32_t *sCount;
-  const uint4 *rec; const uint32_t *contigRecOff;
+  const uint4 *rec; const int32_t *recWposSoA; const uint32_t *contigRecOff;
   int fragLen, cmw, sLimit, shiftA, nBuckets;      // nBuckets: 1024 or 4096 (power of two), directory over h >> shiftA
   uint32_t *cB0, *cE0, *cLast, *cNEv, *cChunks;   // per candidate
   const uint32_t *cOff;                            // first 32-byte slot of the candidate's stream; step k is slot cOff + 32 * k
@@ -345,9 +345,10 @@ __global__ void l2_bounds_kernel(const L2PArgs a)
   if (c < a.C) {
     const int seq = a.cSeq[c];
     const uint32_t lo = a.contigRecOff[seq], hi = a.contigRecOff[seq + 1];
-    const uint32_t b0 = lb_rec(a.rec, lo, hi, a.cStart[c]);
-    const uint32_t e0 = lb_rec(a.rec, b0, hi, rec_wpos(a.rec, b0) + a.cmw);
-    const uint32_t last = lb_rec(a.rec, b0, hi, a.cEnd[c] + a.fragLen);
+    // the three lower_bounds probe the 4-byte position array (8 records per sector), not the 16-byte L2 records
+    const uint32_t b0 = lb_wpos(a.recWposSoA, lo, hi, a.cStart[c]);
+    const uint32_t e0 = lb_wpos(a.recWposSoA, b0, hi, __ldg(&a.recWposSoA[b0]) + a.cmw);
+    const uint32_t last = lb_wpos(a.recWposSoA, b0, hi, a.cEnd[c] + a.fragLen);
     n2 = last - b0;
     const int s = a.sCount[a.cFrag[c]];
     uint32_t nEv = 0;
@@ -418,9 +419,11 @@ l2_events_kernel(const L2PArgs a)
   if (s < 1 || s > a.sLimit) return;
   uint32_t *Q = smem;                                          // s hashes + 3 sentinels
   uint32_t *tab = smem + a.sLimit + 4;                         // L2E_BUCKETS + 1: bucket -> first rank
+  uint2 *QP = reinterpret_cast<uint2 *>(smem + ((a.sLimit + 4 + L2E_BUCKETS + 4 + 1) & ~1));   // {Q[j], Q[j+1]}: both probes in one load
   {
     const uint32_t *Qg = a.fragHash + a.segStart[f];
     for (int i = tid; i < s + 3; i += L2E_THREADS) Q[i] = i < s ? Qg[i] : 0xFFFFFFFFu;
+    for (int i = tid; i < s + 2; i += L2E_THREADS) QP[i] = make_uint2(i < s ? Qg[i] : 0xFFFFFFFFu, i + 1 < s ? Qg[i + 1] : 0xFFFFFFFFu);
     const int NB = a.nBuckets;
     for (int i = tid; i <= NB; i += L2E_THREADS) tab[i] = 0;
     __syncthreads();
@@ -462,7 +465,8 @@ l2_events_kernel(const L2PArgs a)
       const uint32_t h = rc.x;
       // rank of h in Q: directory, then two probes (the sentinels and the sorted order make them unconditional)
       uint32_t j = tab[min(h >> a.shiftA, (uint32_t)(a.nBuckets - 1))];
-      const uint32_t q0 = Q[j], q1 = Q[j + 1];
+      const uint2 qq = QP[j];
+      const uint32_t q0 = qq.x, q1 = qq.y;
       bool match = (q0 == h) || (q1 == h);
       j += (q0 < h) + (q1 < h);
       if (q1 < h) { while (Q[j] < h) j++; match = Q[j] == h; }              // crowded bucket (rare)
@@ -1261,7 +1265,7 @@ void qsketch_map(Ctx *ctx, const Index *ix, const QSketch *const *sketches, int3
               ctx->launches++;
               L2PArgs lp; lp.cFrag = cFrag.p; lp.cSeq = cSeq.p; lp.cStart = cStart.p; lp.cEnd = cEnd.p; lp.C = C;
               lp.fragCandOff = fragCandOff.p; lp.fragHash = fragHash.p; lp.segStart = segStart.p; lp.sCount = sCount.p;
-              lp.rec = ix->rec.p; lp.contigRecOff = ix->contigRecOff.p; lp.fragLen = fragLen; lp.cmw = cmw;
+              lp.rec = ix->rec.p; lp.recWposSoA = ix->wpos.p; lp.contigRecOff = ix->contigRecOff.p; lp.fragLen = fragLen; lp.cmw = cmw;
               // fast path: needs the window links of the index (cmw >= 2) and ranks that fit the event code
               lp.sLimit = (cmw >= 2 && ix->cmw == cmw) ? std::min(smax, L2_SMAX) : 0;
               // bucket width near 0 ~ 2^32 / (s * w): minimizer hashes are minima of w hashes, density w/2^32 at 0
@@ -1307,7 +1311,7 @@ void qsketch_map(Ctx *ctx, const Index *ix, const QSketch *const *sketches, int3
                 BANI_SCRATCH(uint16_t, events, (size_t)totalSteps * 16 + 64);
                 lp.events = events.p; lp.grpOff = grpOff.p;
                 l2_stream_base_kernel<<<nblk(C), 256, 0, st>>>(perm.p, grpOff.p, C, cOff.p); ctx->launches++;
-                const size_t shmE = 4 * ((size_t)lp.sLimit + 4) + 4 * (L2E_BUCKETS + 4);
+                const size_t shmE = 4 * ((size_t)lp.sLimit + 4) + 4 * (L2E_BUCKETS + 4) + 8 + 8 * ((size_t)lp.sLimit + 4);
                 const size_t shmS = (size_t)L2S_WARPS * lp.warpBytes;
                 if (shmE > 200 * 1024 || shmS > 200 * 1024) fail(BANI_ERR_INTERNAL, "L2 shared-memory budget exceeded");
                 if (ctx->first_time((const void *)l2_seq_kernel)) {
