@@ -137,6 +137,7 @@ struct Index {
   DevBuf<uint32_t> hash; DevBuf<int32_t> wpos; DevBuf<int32_t> seqId; DevBuf<uint32_t> link;
   DevBuf<uint4> rec;                 // 16-byte L2 record: x=hash, y=wpos|tie<<31, z=twin link, w=back|fwd<<16 (index.cu)
   int cmw = 0;                       // super-window width the back/fwd fields were computed for
+  int k = 0, w = 0, fragLen = 0;     // parameters of the context the index was built with
   DevBuf<uint32_t> contigRecOff;     // nContigs+1: first record of each contig
   DevBuf<int32_t>  contigGenome;     // nContigs: genome ordinal of a contig (reviseRefIdToGenomeId)
   DevBuf<uint32_t> contigBinOff;     // nContigs+1: prefix of #position-bins per contig (CGI)

@@ -122,6 +122,7 @@ Index *index_build(Ctx *ctx, Genome *const *refs, int32_t nRefs)
   auto ix = std::make_unique<Index>();
   ix->device = ctx->device;
   ix->nGenomes = nRefs;
+  ix->k = k; ix->w = w; ix->fragLen = fragLen;
 
   // ---- contig table over all genomes (every contig consumes a seqId: winSketch.hpp:150,164)
   std::vector<SeqDesc> desc;

@@ -812,7 +812,7 @@ QSketch *qsketch_create(Ctx *ctx, const Genome *const *queries, int32_t nq, cons
   const int k = ctx->prm.kmer_size, w = ctx->prm.window_size, fragLen = ctx->prm.frag_len;
   if (fragLen < 1 || fragLen > 60000) fail(BANI_ERR_LIMIT, "fragment length %d outside the supported range [1, 60000]", fragLen);
   static const bool noReuse = getenv("BANI_NO_SKETCH_REUSE") != nullptr;         // test switch: always hash the queries
-  if (hint && (noReuse || hint->device != ctx->device || hint->M == 0 || !hint->validBits.p)) hint = nullptr;
+  if (hint && (noReuse || hint->device != ctx->device || hint->M == 0 || !hint->validBits.p || hint->k != k || hint->w != w)) hint = nullptr;
   auto member = [&](const Genome *Q) -> int32_t {                                // first contig ordinal inside the hint index
     if (!hint) return -1;
     auto it = hint->members.find(Q->uid);
@@ -1088,6 +1088,8 @@ void qsketch_map(Ctx *ctx, const Index *ix, const QSketch *const *sketches, int3
   const int k = ctx->prm.kmer_size, w = ctx->prm.window_size, fragLen = ctx->prm.frag_len;
   const float pid = ctx->prm.perc_identity;
   if (ix->device != ctx->device) fail(BANI_ERR_ARG, "index lives on another device");
+  if (ix->k != k || ix->w != w || ix->fragLen != fragLen)
+    fail(BANI_ERR_ARG, "index was built with other parameters (k %d w %d fragLen %d)", ix->k, ix->w, ix->fragLen);
   if (wantCgi && fragLen <= 20) fail(BANI_ERR_ARG, "fragment length must exceed 20 for the identity reduction");
   const int cmw = fragLen - (w - 1) - (k - 1);         // computeMap.hpp:427
   out.ctr = bani_map_counters{};
