@@ -9,8 +9,9 @@ Workload (config.workload): BASELINE.json configs[2], "Many-to-many: 1000 x 1000
 bacterial genomes, k=16, fragLen=3000": 50 clusters x 20 strains, strain m = cluster ancestor with iid
 substitutions at rate 0.6 % * m, one contig per genome, Q = R = the same 1000 genomes.
 One "step" = one pass of the hot path over the whole batch: HP1 (index build over this rank's reference
-shard) + HP2 (all queries mapped against it) + the per-pair reduction + (N > 1) the gather of the dense
-per-pair tables.  value = pairs / step time with the genomes already packed in HBM; e2e = the same through
+shard) + HP2 (all queries mapped against it) + the per-pair reduction; for N > 1 each rank sketches 1/N of the
+queries, the sketches are all-gathered over NCCL, every rank maps all of them against its shard, and the dense
+per-pair tables are gathered at the end.  value = pairs / step time with the genomes already packed in HBM; e2e = the same through
 the C ABI from pinned HOST buffers (H2D + 2-bit packing inside the timed region, results copied back).
 """
 import argparse
