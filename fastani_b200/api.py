@@ -10,6 +10,7 @@ in validateInputFiles).  No CPU fallback: a missing library or GPU raises.
 """
 import ctypes as C
 import os
+import weakref
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -74,6 +75,7 @@ def load_library():
         "bani_ctx_sync": (C.c_int, [vp]),
         "bani_ctx_stream": (vp, [vp]),
         "bani_ctx_launch_count": (u64, [vp]),
+        "bani_ctx_set_flag": (C.c_int, [vp, C.c_char_p, i64]),
         "bani_ctx_profile_enable": (C.c_int, [vp, C.c_int]),
         "bani_ctx_profile_read": (C.c_int, [vp, vp, vp, vp, vp, i32, P(i32)]),
         "bani_host_alloc": (C.c_int, [C.c_size_t, P(vp)]),
@@ -111,7 +113,7 @@ def load_library():
 EXPORTED_SYMBOLS = [
     "bani_last_error", "bani_version", "bani_params_default", "bani_recommended_window_size", "bani_device_count",
     "bani_stat_min_hits_relaxed", "bani_stat_identity", "bani_ctx_create", "bani_ctx_destroy", "bani_ctx_params",
-    "bani_ctx_sync", "bani_ctx_stream", "bani_ctx_launch_count", "bani_ctx_profile_enable", "bani_ctx_profile_read", "bani_host_alloc", "bani_host_free", "bani_genome_create",
+    "bani_ctx_sync", "bani_ctx_stream", "bani_ctx_launch_count", "bani_ctx_set_flag", "bani_ctx_profile_enable", "bani_ctx_profile_read", "bani_host_alloc", "bani_host_free", "bani_genome_create",
     "bani_genome_create_batch", "bani_genome_destroy", "bani_genome_info", "bani_genome_decode", "bani_index_build",
     "bani_index_destroy", "bani_index_stats", "bani_index_minimizers", "bani_index_lookup", "bani_map_genome",
     "bani_map_cgi", "bani_free", "bani_synth_genome", "bani_qsketch_create", "bani_qsketch_destroy", "bani_qsketch_info",
@@ -181,6 +183,10 @@ class Context:
     def launch_count(self):
         return int(self.lib.bani_ctx_launch_count(self.h))
 
+    def set_flag(self, name, value):
+        """bani_ctx_set_flag: "sketch_reuse", "max_hits_per_piece", "frag_l1_max", "l2e_buckets"."""
+        _check(self.lib.bani_ctx_set_flag(self.h, name.encode(), int(value)))
+
     def profile(self, on=True):
         _check(self.lib.bani_ctx_profile_enable(self.h, 1 if on else 0))
 
@@ -247,18 +253,14 @@ class Context:
         p = C.c_void_p()
         _check(self.lib.bani_host_alloc(nbytes, C.byref(p)))
         buf = (C.c_uint8 * max(nbytes, 1)).from_address(p.value)
-        arr = np.frombuffer(buf, dtype=np.uint8, count=nbytes)
-        _PINNED[p.value] = (self.lib, buf)
-        return arr
+        weakref.finalize(buf, self.lib.bani_host_free, p.value)      # the array's base: page-locked memory goes back with it
+        return np.frombuffer(buf, dtype=np.uint8, count=nbytes)
 
     def synth_genome(self, seed, ancestor, strain, ppm, length, out=None):
         if out is None:
             out = np.empty(length, np.uint8)
         _check(self.lib.bani_synth_genome(self.h, seed, ancestor, strain, ppm, length, out.ctypes.data))
         return out
-
-
-_PINNED = {}
 
 
 class Genome:

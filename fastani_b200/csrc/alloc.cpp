@@ -45,9 +45,10 @@ void dev_cache_flush(int dev)
   }
 }
 
-void *dev_alloc(size_t bytes, cudaStream_t st, size_t *granted)
+void *dev_alloc(size_t bytes, cudaStream_t st, size_t *granted, int *devOut)
 {
   int dev = 0; cudaGetDevice(&dev);
+  *devOut = dev;
   const size_t rb = round_size(bytes);
   *granted = rb;
   {
@@ -67,10 +68,11 @@ void *dev_alloc(size_t bytes, cudaStream_t st, size_t *granted)
   return p;
 }
 
-void dev_free(void *p, size_t granted, cudaStream_t st)
+void dev_free(void *p, size_t granted, cudaStream_t st, int dev)
 {
   if (!p) return;
-  int dev = 0; cudaGetDevice(&dev);
+  // keyed by the device the block was ALLOCATED on (recorded in DevBuf), not by the caller's current device: a host
+  // thread that drives several GPUs may destroy an object of device A while device B is current
   std::lock_guard<std::mutex> lk(g_mu);
   g_free.emplace(Key{dev, st, granted}, p);
 }

@@ -87,6 +87,13 @@ int bani_ctx_create(int device, const bani_params *p, bani_ctx **out)
   cudaDeviceProp prop;
   BANI_CUDA(cudaGetDeviceProperties(&prop, device));
   c->c.smCount = prop.multiProcessorCount;
+  {   // defaults of the run-time switches from the environment (see CtxFlags)
+    CtxFlags &f = c->c.flags;
+    if (getenv("BANI_NO_SKETCH_REUSE")) f.sketchReuse = 0;
+    if (const char *e = getenv("BANI_MAX_HITS_PER_PIECE")) f.maxHitsPerPiece = std::max(1ll, atoll(e));
+    if (const char *e = getenv("BANI_FRAG_L1_MAX")) f.fragL1Max = std::max(0ll, atoll(e));
+    if (const char *e = getenv("BANI_L2E_BUCKETS")) { const int v = atoi(e); if (v == 1024 || v == 4096) f.l2eBuckets = v; }
+  }
   dev_cache_flush(device);                   // blocks cached under streams of destroyed contexts
   BANI_CUDA(cudaStreamCreateWithFlags(&c->c.stream, cudaStreamNonBlocking));
   *out = c.release();
@@ -119,6 +126,21 @@ int bani_ctx_sync(bani_ctx *ctx)
   if (!ctx) fail(BANI_ERR_ARG, "null context");
   BANI_CUDA(cudaSetDevice(ctx->c.device));
   BANI_CUDA(cudaStreamSynchronize(ctx->c.stream));
+  return BANI_OK;
+  BANI_CATCH
+}
+
+int bani_ctx_set_flag(bani_ctx *ctx, const char *name, int64_t value)
+{
+  BANI_TRY
+  if (!ctx || !name) fail(BANI_ERR_ARG, "null argument");
+  CtxFlags &f = ctx->c.flags;
+  const std::string n(name);
+  if (n == "sketch_reuse") f.sketchReuse = value != 0;
+  else if (n == "max_hits_per_piece") { if (value < 1) fail(BANI_ERR_ARG, "max_hits_per_piece must be positive"); f.maxHitsPerPiece = value; }
+  else if (n == "frag_l1_max") { if (value < 0) fail(BANI_ERR_ARG, "frag_l1_max must not be negative"); f.fragL1Max = value; }
+  else if (n == "l2e_buckets") { if (value != 0 && value != 1024 && value != 4096) fail(BANI_ERR_ARG, "l2e_buckets must be 0, 1024 or 4096"); f.l2eBuckets = (int)value; }
+  else fail(BANI_ERR_ARG, "unknown flag '%s'", name);
   return BANI_OK;
   BANI_CATCH
 }
@@ -373,7 +395,12 @@ int bani_qsketch_create(bani_ctx *ctx, bani_genome *const *queries, int32_t n_qu
   BANI_CATCH
 }
 
-void bani_qsketch_destroy(bani_qsketch *qs) { if (qs) { delete qs->qs; delete qs; } }
+void bani_qsketch_destroy(bani_qsketch *qs)
+{
+  if (!qs) return;
+  if (qs->qs) { cudaSetDevice(qs->qs->device); delete qs->qs; }
+  delete qs;
+}
 
 int bani_qsketch_info(const bani_qsketch *qs, int32_t *n_queries, uint64_t *n_fragments, uint64_t *n_hashes, uint64_t *export_bytes)
 {

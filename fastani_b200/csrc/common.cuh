@@ -34,27 +34,27 @@ void set_last_error(const std::string &m);
 // ---------------------------------------------------------------- device memory
 // DevBuf owns a block from the caching allocator of alloc.cpp (freed blocks are reused on the same
 // stream; the driver is only called on a miss).
-void *dev_alloc(size_t bytes, cudaStream_t st, size_t *granted);
-void  dev_free(void *p, size_t granted, cudaStream_t st);
+void *dev_alloc(size_t bytes, cudaStream_t st, size_t *granted, int *dev);
+void  dev_free(void *p, size_t granted, cudaStream_t st, int dev);      // dev = the device the block was allocated on
 void  dev_cache_flush(int dev);
 
 template <typename T>
 struct DevBuf {
-  T *p = nullptr; size_t n = 0; cudaStream_t st = nullptr; size_t granted = 0;
+  T *p = nullptr; size_t n = 0; cudaStream_t st = nullptr; size_t granted = 0; int dev = -1;
   DevBuf() {}
   DevBuf(size_t n_, cudaStream_t s) { alloc(n_, s); }
   DevBuf(const DevBuf &) = delete; DevBuf &operator=(const DevBuf &) = delete;
-  DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), st(o.st), granted(o.granted) { o.p = nullptr; o.n = 0; }
+  DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), st(o.st), granted(o.granted), dev(o.dev) { o.p = nullptr; o.n = 0; }
   DevBuf &operator=(DevBuf &&o) noexcept
-  { if (this != &o) { release(); p = o.p; n = o.n; st = o.st; granted = o.granted; o.p = nullptr; o.n = 0; } return *this; }
+  { if (this != &o) { release(); p = o.p; n = o.n; st = o.st; granted = o.granted; dev = o.dev; o.p = nullptr; o.n = 0; } return *this; }
   ~DevBuf() { release(); }
   void alloc(size_t n_, cudaStream_t s)
   {
     release(); n = n_; st = s;
     if (n == 0) return;
-    p = (T *)dev_alloc(n * sizeof(T), s, &granted);
+    p = (T *)dev_alloc(n * sizeof(T), s, &granted, &dev);
   }
-  void release() { if (p) { dev_free(p, granted, st); p = nullptr; } n = 0; }
+  void release() { if (p) { dev_free(p, granted, st, dev); p = nullptr; } n = 0; }
   size_t bytes() const { return n * sizeof(T); }
 };
 
@@ -165,10 +165,20 @@ struct View {
   void release() {}
 };
 
+// Run-time switches of a context (bani_ctx_set_flag); the defaults can also be set through the environment
+// (BANI_NO_SKETCH_REUSE, BANI_MAX_HITS_PER_PIECE, BANI_FRAG_L1_MAX, BANI_L2E_BUCKETS), read when the context is created.
+struct CtxFlags {
+  int sketchReuse = 1;                        // stage A': fragment sketches of index members are read from the index
+  long long maxHitsPerPiece = 3ll << 29;      // a piece that gathers more index hits is split at a query boundary
+  long long fragL1Max = 8192;                 // hits per fragment handled inside one CTA (<= FRAG_L1_MAX)
+  int l2eBuckets = 0;                         // 0 = adaptive; 1024 / 4096 force the size of the L2 rank directory
+};
+
 struct Ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   bani_params prm{};
+  CtxFlags flags;
   int smCount = 0;
   StatLut lut;
   DevBuf<int32_t> d_minHits; DevBuf<uint32_t> d_rowOff; DevBuf<float> d_ident, d_upper;

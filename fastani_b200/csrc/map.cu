@@ -305,6 +305,7 @@ l2_kernel(const L2Args a)
 // a "match" at rank s: they toggle the presence bit of the sentinel rank s, which no pivot position ever counts.
 // A count reaching 64 (or s > 2047) hands the candidate to the exact global-memory kernel above.
 static constexpr int L2_SMAX = 2047;
+static constexpr int L2_SHM_BUDGET = 200 * 1024;      // dynamic shared memory granted to l2_events_kernel / l2_seq_kernel
 static constexpr uint32_t EV_M = 1u, EV_D = 2u, EV_S = 4u, EV_JMASK = 0xFFE0u;
 __host__ __device__ __forceinline__ uint32_t ev_rank(uint32_t j) { return j << 5; }
 
@@ -811,7 +812,7 @@ QSketch *qsketch_create(Ctx *ctx, const Genome *const *queries, int32_t nq, cons
   cudaStream_t st = ctx->stream;
   const int k = ctx->prm.kmer_size, w = ctx->prm.window_size, fragLen = ctx->prm.frag_len;
   if (fragLen < 1 || fragLen > 60000) fail(BANI_ERR_LIMIT, "fragment length %d outside the supported range [1, 60000]", fragLen);
-  static const bool noReuse = getenv("BANI_NO_SKETCH_REUSE") != nullptr;         // test switch: always hash the queries
+  const bool noReuse = !ctx->flags.sketchReuse;                                  // switch: always hash the queries
   if (hint && (noReuse || hint->device != ctx->device || hint->M == 0 || !hint->validBits.p || hint->k != k || hint->w != w)) hint = nullptr;
   auto member = [&](const Genome *Q) -> int32_t {                                // first contig ordinal inside the hint index
     if (!hint) return -1;
@@ -991,6 +992,22 @@ void qsketch_export(Ctx *ctx, const QSketch *qs, void *devBuf, uint64_t cap)
   BANI_CUDA(cudaStreamSynchronize(st));              // h must outlive the copy
 }
 
+// A buffer that arrived from another rank is not trusted: sizes are checked against `bytes` before anything is
+// allocated or copied, and the per-fragment tables are checked on the device before they are used as indices.
+__global__ void qsketch_validate_kernel(const uint32_t *segStart, const int32_t *sCount, const int32_t *fragQuery, int32_t F, uint64_t T,
+                                        int smax, int nq, int *bad)
+{
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= F) return;
+  const uint32_t a = segStart[f], b = segStart[f + 1];
+  const int s = sCount[f];
+  bool ok = a <= b && (uint64_t)b <= T && s >= 0 && s <= smax && (uint32_t)s == b - a && fragQuery[f] >= 0 && fragQuery[f] < nq;
+  if (f == 0 && a != 0) ok = false;
+  if (f == F - 1 && (uint64_t)b != T) ok = false;
+  if (f > 0 && fragQuery[f] < fragQuery[f - 1]) ok = false;
+  if (!ok) atomicExch(bad, 1);
+}
+
 QSketch *qsketch_import(Ctx *ctx, const void *devBuf, uint64_t bytes)
 {
   cudaStream_t st = ctx->stream;
@@ -1001,8 +1018,10 @@ QSketch *qsketch_import(Ctx *ctx, const void *devBuf, uint64_t bytes)
   if (h0[0] != QS_MAGIC || h0[6] > bytes) fail(BANI_ERR_ARG, "not a query sketch buffer (or truncated)");
   if ((int)h0[3] != ctx->prm.kmer_size || (int)h0[4] != ctx->prm.window_size || (int)h0[5] != ctx->prm.frag_len)
     fail(BANI_ERR_ARG, "query sketch was built with other parameters (k %d w %d fragLen %d)", (int)h0[3], (int)h0[4], (int)h0[5]);
-  const uint64_t nP = h0[1], nQ = h0[2];
+  const uint64_t nP = h0[1], nQ = h0[2], total = h0[6];
+  if (nP > (1ull << 24) || nQ > (1ull << 31)) fail(BANI_ERR_ARG, "corrupt query sketch buffer (header counts)");
   const uint64_t hdrBytes = 64 + pad16(16 * nQ) + 48 * nP;
+  if (hdrBytes > total) fail(BANI_ERR_ARG, "query sketch buffer truncated (header)");
   std::vector<uint8_t> h(hdrBytes);
   BANI_CUDA(cudaMemcpyAsync(h.data(), devBuf, hdrBytes, cudaMemcpyDeviceToHost, st));
   BANI_CUDA(cudaStreamSynchronize(st));
@@ -1016,24 +1035,42 @@ QSketch *qsketch_import(Ctx *ctx, const void *devBuf, uint64_t bytes)
   const uint64_t *ph = (const uint64_t *)(h.data() + 64 + pad16(16 * nQ));
   const uint8_t *d = (const uint8_t *)devBuf;
   uint64_t o = hdrBytes;
+  DevBuf<int> d_bad(1, st);
+  BANI_CUDA(cudaMemsetAsync(d_bad.p, 0, 4, st));
+  uint64_t covered = 0;
   for (uint64_t i = 0; i < nP; i++) {
     auto pc = std::make_unique<QPiece>();
-    pc->F = (int32_t)ph[6 * i]; pc->T = ph[6 * i + 1]; pc->smax = (int)ph[6 * i + 2]; pc->q0 = (int)ph[6 * i + 3]; pc->nq = (int)ph[6 * i + 4];
-    if (pc->q0 < 0 || pc->nq < 0 || (uint64_t)pc->q0 + (uint64_t)pc->nq > nQ) fail(BANI_ERR_ARG, "corrupt query sketch buffer");
-    for (int q = 0; q < pc->nq; q++) pc->qFragOff.push_back(((const int32_t *)(h.data() + 64 + 16 * (uint64_t)(pc->q0 + q)))[1]);
+    const uint64_t F64 = ph[6 * i], T64 = ph[6 * i + 1], smax64 = ph[6 * i + 2], q064 = ph[6 * i + 3], nq64 = ph[6 * i + 4];
+    if (F64 > FRAG_MAX || T64 > 0xfffffff0ull || smax64 > (uint64_t)SU_CAP || q064 != covered || nq64 > nQ - q064 || T64 > F64 * (uint64_t)SU_CAP)
+      fail(BANI_ERR_ARG, "corrupt query sketch buffer (piece %llu)", (unsigned long long)i);
+    pc->F = (int32_t)F64; pc->T = T64; pc->smax = (int)smax64; pc->q0 = (int)q064; pc->nq = (int)nq64;
+    covered += nq64;
+    for (int q = 0; q < pc->nq; q++) {
+      const int32_t fo = ((const int32_t *)(h.data() + 64 + 16 * (uint64_t)(pc->q0 + q)))[1];
+      if (fo < 0 || fo > pc->F || (q > 0 && fo < pc->qFragOff.back()) || (q == 0 && fo != 0)) fail(BANI_ERR_ARG, "corrupt query sketch buffer (fragment offsets)");
+      pc->qFragOff.push_back(fo);
+    }
     pc->qFragOff.push_back(pc->F);
     if (pc->F > 0) {
-      auto get = [&](void *p, uint64_t b) { if (o + b > bytes) fail(BANI_ERR_ARG, "query sketch buffer truncated");
-                                             BANI_CUDA(cudaMemcpyAsync(p, d + o, b, cudaMemcpyDeviceToDevice, st)); o += pad16(b); };
+      if (pc->nq == 0) fail(BANI_ERR_ARG, "corrupt query sketch buffer (fragments without a query)");
+      const uint64_t need = pad16(4ull * (pc->F + 1)) + 3 * pad16(4ull * pc->F) + pad16(4ull * std::max<uint64_t>(pc->T, 1));
+      if (o + need > total) fail(BANI_ERR_ARG, "query sketch buffer truncated");
+      auto get = [&](void *p, uint64_t b) { BANI_CUDA(cudaMemcpyAsync(p, d + o, b, cudaMemcpyDeviceToDevice, st)); o += pad16(b); };
       pc->segStart.alloc((size_t)pc->F + 1, st); pc->sCount.alloc(pc->F, st); pc->fragQuery.alloc(pc->F, st); pc->fragSeqId.alloc(pc->F, st);
       pc->fragHash.alloc(std::max<uint64_t>(pc->T, 1), st);
       get(pc->segStart.p, 4ull * (pc->F + 1)); get(pc->sCount.p, 4ull * pc->F); get(pc->fragQuery.p, 4ull * pc->F);
       get(pc->fragSeqId.p, 4ull * pc->F); get(pc->fragHash.p, 4ull * std::max<uint64_t>(pc->T, 1));
+      qsketch_validate_kernel<<<nblk(pc->F), 256, 0, st>>>(pc->segStart.p, pc->sCount.p, pc->fragQuery.p, pc->F, pc->T, pc->smax, pc->nq, d_bad.p);
+      ctx->launches++;
     }
     qs->F += pc->F; qs->T += pc->T;
     qs->pieces.push_back(std::move(pc));
   }
+  if (covered != nQ) fail(BANI_ERR_ARG, "corrupt query sketch buffer (queries not covered by the pieces)");
+  int bad = 0;
+  BANI_CUDA(cudaMemcpyAsync(&bad, d_bad.p, 4, cudaMemcpyDeviceToHost, st));
   BANI_CUDA(cudaStreamSynchronize(st));
+  if (bad) fail(BANI_ERR_ARG, "corrupt query sketch buffer (fragment tables)");
   return qs.release();
 }
 
@@ -1111,8 +1148,7 @@ void qsketch_map(Ctx *ctx, const Index *ix, const QSketch *const *sketches, int3
    if (!qs) fail(BANI_ERR_ARG, "null query sketch");
    if (qs->device != ctx->device) fail(BANI_ERR_ARG, "query sketch lives on another device");
    if (qs->k != k || qs->w != w || qs->fragLen != fragLen) fail(BANI_ERR_ARG, "query sketch was built with other parameters");
-   static const unsigned long long maxHits = [] { const char *e = getenv("BANI_MAX_HITS_PER_PIECE");          // test switch
-                                                 return e ? (unsigned long long)atoll(e) : (3ull << 29); }();           // 1.6 G hits per pass
+   const unsigned long long maxHits = (unsigned long long)std::max(1ll, ctx->flags.maxHitsPerPiece);           // 1.6 G hits per pass by default
    std::deque<const QPiece *> work;
    std::vector<std::unique_ptr<QPiece>> slices;
    for (const auto &pcp : qs->pieces) work.push_back(pcp.get());
@@ -1174,8 +1210,7 @@ void qsketch_map(Ctx *ctx, const Index *ix, const QSketch *const *sketches, int3
           BANI_SCRATCH(int32_t, stSeq, N);
           BANI_SCRATCH(int32_t, stStart, N);
           BANI_SCRATCH(int32_t, stEnd, N);
-          static const long long maxFast = [] { const char *e = getenv("BANI_FRAG_L1_MAX"); long long v = e ? atoll(e) : (long long)FRAG_L1_MAX;
-                                                return std::max(0ll, std::min(v, (long long)FRAG_L1_MAX)); }();
+          const long long maxFast = std::max(0ll, std::min(ctx->flags.fragL1Max, (long long)FRAG_L1_MAX));
           uint32_t hClass[FRAG_NCLASS + 2];
           { Stage sg(ctx, "frag_l1", 12.0 * N);                // 4 B list entry + 8 B (seqId, wpos) per hit
             frag_classify(ctx, segStart.p, hitOff.p, F, candCount.p, fragClass.p, classCount.p, classList.p, (unsigned long long)maxFast);
@@ -1269,10 +1304,11 @@ void qsketch_map(Ctx *ctx, const Index *ix, const QSketch *const *sketches, int3
               lp.fragCandOff = fragCandOff.p; lp.fragHash = fragHash.p; lp.segStart = segStart.p; lp.sCount = sCount.p;
               lp.rec = ix->rec.p; lp.recWposSoA = ix->wpos.p; lp.contigRecOff = ix->contigRecOff.p; lp.fragLen = fragLen; lp.cmw = cmw;
               // fast path: needs the window links of the index (cmw >= 2) and ranks that fit the event code
-              lp.sLimit = (cmw >= 2 && ix->cmw == cmw) ? std::min(smax, L2_SMAX) : 0;
+              // (and whose per-warp state fits the shared-memory budget of l2_seq_kernel: larger sketches take l2_kernel)
+              lp.sLimit = (cmw >= 2 && ix->cmw == cmw) ? std::min(std::min(smax, L2_SMAX), L2_SHM_BUDGET / (L2S_WARPS * 32) - 2) : 0;
               // bucket width near 0 ~ 2^32 / (s * w): minimizer hashes are minima of w hashes, density w/2^32 at 0
               lp.nBuckets = ((uint64_t)C >= 8ull * (uint64_t)F) ? L2E_BUCKETS : 1024;      // few candidates per fragment: building a big directory is not worth it
-              { static const int forced = [] { const char *e = getenv("BANI_L2E_BUCKETS"); return e ? atoi(e) : 0; }();      // test switch
+              { const int forced = ctx->flags.l2eBuckets;
                 if (forced == 1024 || forced == L2E_BUCKETS) lp.nBuckets = forced; }
               { int sh = lp.nBuckets == L2E_BUCKETS ? 20 : 22; while (sh > 8 && ((uint64_t)std::max(smax, 1) * (uint64_t)w << sh) > ((1ull << 32) * (uint64_t)(L2E_BUCKETS / lp.nBuckets))) sh--; lp.shiftA = sh; }
               lp.warpBytes = (uint32_t)(std::max(lp.sLimit, 1) + 1) * 32u;      // one state byte per rank 0..s and lane
@@ -1315,10 +1351,10 @@ void qsketch_map(Ctx *ctx, const Index *ix, const QSketch *const *sketches, int3
                 l2_stream_base_kernel<<<nblk(C), 256, 0, st>>>(perm.p, grpOff.p, C, cOff.p); ctx->launches++;
                 const size_t shmE = 4 * ((size_t)lp.sLimit + 4) + 4 * (L2E_BUCKETS + 4) + 8 + 8 * ((size_t)lp.sLimit + 4);
                 const size_t shmS = (size_t)L2S_WARPS * lp.warpBytes;
-                if (shmE > 200 * 1024 || shmS > 200 * 1024) fail(BANI_ERR_INTERNAL, "L2 shared-memory budget exceeded");
+                if (shmE > (size_t)L2_SHM_BUDGET || shmS > (size_t)L2_SHM_BUDGET) fail(BANI_ERR_INTERNAL, "L2 shared-memory budget exceeded");
                 if (ctx->first_time((const void *)l2_seq_kernel)) {
-                  BANI_CUDA(cudaFuncSetAttribute(l2_events_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                  BANI_CUDA(cudaFuncSetAttribute(l2_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                  BANI_CUDA(cudaFuncSetAttribute(l2_events_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L2_SHM_BUDGET));
+                  BANI_CUDA(cudaFuncSetAttribute(l2_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L2_SHM_BUDGET));
                   BANI_CUDA(cudaFuncSetAttribute(l2_seq_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
                 }
                 sgb.stop();

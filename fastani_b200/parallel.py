@@ -21,46 +21,60 @@ def global_ref_id(local_id, world, rank):
     return local_id * world + rank
 
 
-def dense_tables(cgi_results, n_queries, n_local_refs):
-    """CGI result rows of one shard -> dense [n_queries, n_local_refs] (count, identity) tables."""
+def dense_tables(cgi_results, n_queries, n_local_refs, total_fragments=None):
+    """CGI result rows of one shard -> dense [n_queries, n_local_refs] (count, identity) tables and the per-query
+    totalQueryFragments (taken from `total_fragments` when given, else from the rows; 0 = unknown on this shard)."""
     cnt = np.zeros((n_queries, max(n_local_refs, 0)), np.int32)
     idn = np.zeros((n_queries, max(n_local_refs, 0)), np.float32)
+    tot = np.zeros(n_queries, np.int32)
     if len(cgi_results):
         q = cgi_results["qryGenomeId"]; r = cgi_results["refGenomeId"]
         cnt[q, r] = cgi_results["countSeq"]
         idn[q, r] = cgi_results["identity"]
-    return cnt, idn
+        tot[q] = cgi_results["totalQueryFragments"]
+    if total_fragments is not None:
+        tot[:len(total_fragments)] = np.asarray(total_fragments, np.int64).astype(np.int32)
+    return cnt, idn, tot
 
 
 def merge_shards(tables, n_queries, n_refs, world):
-    """tables[g] = (count, identity) of shard g, shapes [n_queries, len(shard_refs(n_refs, world, g))].
-    Returns the global [n_queries, n_refs] tables."""
+    """tables[g] = (count, identity[, totals]) of shard g, shapes [n_queries, len(shard_refs(n_refs, world, g))].
+    Returns the global [n_queries, n_refs] tables (and the element-wise maximum of the totals when present)."""
     cnt = np.zeros((n_queries, n_refs), np.int32)
     idn = np.zeros((n_queries, n_refs), np.float32)
-    for g, (c, i) in enumerate(tables):
+    tot = None
+    for g, t in enumerate(tables):
+        c, i = t[0], t[1]
         cols = shard_refs(n_refs, world, g)
         if cols:
             cnt[:, cols] = c[:, :len(cols)]
             idn[:, cols] = i[:, :len(cols)]
-    return cnt, idn
+        if len(t) > 2 and t[2] is not None:
+            tot = t[2].copy() if tot is None else np.maximum(tot, t[2])
+    return (cnt, idn) if tot is None else (cnt, idn, tot)
 
 
-def gather_tables(cnt_local, idn_local, n_refs, world, rank, dist=None, device=None):
-    """All-gather of the per-shard tables over torch.distributed (NCCL on GPUs, gloo on CPU).
-    Shards are padded to the largest shard so that one collective per table suffices."""
+def gather_tables(cnt_local, idn_local, n_refs, world, rank, dist=None, device=None, tot=None):
+    """All-gather of the per-shard tables over torch.distributed (NCCL on GPUs, gloo on CPU): shards are padded to the
+    largest shard and count / identity bits / totals travel as ONE int32 tensor in one collective.
+    Returns (count, identity) or, when `tot` is given, (count, identity, totals)."""
     n_queries = cnt_local.shape[0]
     if world == 1 or dist is None:
-        return merge_shards([(cnt_local, idn_local)], n_queries, n_refs, 1)
+        return merge_shards([(cnt_local, idn_local, tot)], n_queries, n_refs, 1)
     import torch
     width = (n_refs + world - 1) // world
-    pc = np.zeros((n_queries, width), np.int32); pi = np.zeros((n_queries, width), np.float32)
-    pc[:, :cnt_local.shape[1]] = cnt_local; pi[:, :idn_local.shape[1]] = idn_local
-    tc = torch.from_numpy(pc); ti = torch.from_numpy(pi)
+    pack = np.zeros((n_queries, 2 * width + 1), np.int32)
+    pack[:, :cnt_local.shape[1]] = cnt_local
+    pack[:, width:width + idn_local.shape[1]] = idn_local.view(np.int32)
+    if tot is not None:
+        pack[:, 2 * width] = tot
+    t = torch.from_numpy(pack)
     if device is not None:
-        tc = tc.to(device); ti = ti.to(device)
-    gc = [torch.empty_like(tc) for _ in range(world)]; gi = [torch.empty_like(ti) for _ in range(world)]
-    dist.all_gather(gc, tc); dist.all_gather(gi, ti)
-    tables = [(gc[g].cpu().numpy(), gi[g].cpu().numpy()) for g in range(world)]
+        t = t.to(device)
+    out = torch.empty((world * t.shape[0], t.shape[1]), dtype=t.dtype, device=t.device)      # rank-major concatenation
+    dist.all_gather_into_tensor(out, t)
+    o = out.cpu().numpy().reshape(world, t.shape[0], t.shape[1])
+    tables = [(o[g][:, :width], o[g][:, width:2 * width].view(np.float32), o[g][:, 2 * width] if tot is not None else None) for g in range(world)]
     return merge_shards(tables, n_queries, n_refs, world)
 
 

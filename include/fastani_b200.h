@@ -114,6 +114,11 @@ BANI_API int  bani_ctx_sync(bani_ctx *ctx);
 /* Raw CUDA stream (cudaStream_t) every launch of this context goes to; for event timing. */
 BANI_API void *bani_ctx_stream(bani_ctx *ctx);
 
+/* Run-time switches of a context.  name: "sketch_reuse" (1 = read the fragment sketches of index members from the
+ * index, 0 = always hash the query fragments: what a run with --ql != --rl does), "max_hits_per_piece",
+ * "frag_l1_max", "l2e_buckets" (tuning / test switches of the mapping pipeline; results never depend on them). */
+BANI_API int  bani_ctx_set_flag(bani_ctx *ctx, const char *name, int64_t value);
+
 /* Per-stage device timing.  When enabled, every stage of HP1/HP2 is bracketed by CUDA events on
  * the context's stream; bani_ctx_profile_read() synchronises, sums the elapsed time, launch count and
  * algorithmic bytes per stage name since the last read, and clears the record.  names: n_max

@@ -30,17 +30,22 @@ def run(ref_ids):
     rec, sbf, _ = po.sketch_genomes(refs, 16, 24)
     ix = po.Index(rec)
     cnt = np.zeros((len(queries), len(refs)), np.int32); idn = np.zeros((len(queries), len(refs)), np.float32)
+    tq = np.zeros(len(queries), np.int32)
     for qi, q in enumerate(queries):
         rows, tot, _ = po.map_genome(ix, q, 16, 24, 3000)
         for g, c, i in po.cgi(rows, sbf, 3000):
             cnt[qi, g] = c; idn[qi, g] = i
-    return cnt, idn
+            tq[qi] = tot                      # as the CGI rows carry it: known only where the query has a row
+    return cnt, idn, tq
 
 mine = parallel.shard_refs(len(genomes), world, rank)
-c, i = run(mine)
-gc, gi = parallel.gather_tables(c, i, len(genomes), world, rank, dist=dist)
+c, i, t = run(mine)
+gc, gi, gt = parallel.gather_tables(c, i, len(genomes), world, rank, dist=dist, tot=t)
+gc2, gi2 = parallel.gather_tables(c, i, len(genomes), world, rank, dist=dist)
+assert (gc2 == gc).all() and (gi2.view(np.uint32) == gi.view(np.uint32)).all()
 if rank == 0:
-    fc, fi = run(list(range(len(genomes))))
+    fc, fi, ft = run(list(range(len(genomes))))
+    assert (gt == ft).all() and (ft == L // 3000).all(), (gt, ft)
     assert (gc == fc).all() and (gi.view(np.uint32) == fi.view(np.uint32)).all(), (gc, fc)
     assert int((fc > 0).sum()) >= 7
     print("DIST_OK", int((fc > 0).sum()))

@@ -163,7 +163,7 @@ def test_many_to_many_synthetic_vs_oracle_and_shard_invariance():
     n = len(hs)
     sk = fb.Sketch(ctx, hs)
     res, tot, ctr = fb.compute_cgi(ctx, sk, hs)
-    cnt, idn = parallel.dense_tables(res, n, n)
+    cnt, idn, _ = parallel.dense_tables(res, n, n)
     # oracle
     rec, sbf, _ = po.sketch_genomes(genomes, 16, 24)
     ix = po.Index(rec)
@@ -189,7 +189,8 @@ def test_many_to_many_synthetic_vs_oracle_and_shard_invariance():
         ids = parallel.shard_refs(n, G, g)
         r, _, _ = fb.compute_cgi(ctx, fb.Sketch(ctx, [hs[i] for i in ids]), hs)
         tabs.append(parallel.dense_tables(r, n, len(ids)))
-    mc, mi = parallel.merge_shards(tabs, n, n, G)
+    mc, mi, mt = parallel.merge_shards(tabs, n, n, G)
+    assert (mt == np.asarray(tot, np.int64)).all()
     assert (mc == cnt).all() and (mi.view(np.uint32) == idn.view(np.uint32)).all()
 
 
@@ -208,7 +209,7 @@ def test_full_size_properties():
     assert abs(len(rec) / (2 * L) - 2 / 25) < 0.002                    # density 2/(w+1)
     assert st["n_unique"] == len(np.unique(rec["hash"]))
     res, tot, _ = fb.compute_cgi(ctx, sk, [ga, gb])
-    cnt, idn = parallel.dense_tables(res, 2, 2)
+    cnt, idn, _ = parallel.dense_tables(res, 2, 2)
     assert int(tot[0]) == L // 3000 and cnt[0, 0] >= tot[0] - 1 and cnt[1, 1] >= tot[1] - 1
     assert idn[0, 0] > 99.99 and idn[1, 1] > 99.99
     assert cnt[0, 1] > 0.95 * tot[0] and abs(float(idn[0, 1]) - 97.6) < 0.5
