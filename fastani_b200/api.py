@@ -82,6 +82,8 @@ def load_library():
         "bani_host_free": (None, [vp]),
         "bani_genome_create": (C.c_int, [vp, i32, vp, vp, P(vp)]),
         "bani_genome_create_batch": (C.c_int, [vp, i32, vp, vp, vp, P(vp)]),
+        "bani_pack_contig": (C.c_int, [vp, i64, vp, vp, vp, u64, P(u64)]),
+        "bani_genome_create_packed_batch": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, P(vp)]),
         "bani_genome_destroy": (None, [vp]),
         "bani_genome_info": (C.c_int, [vp, P(i32), P(u64), P(u64), P(u64)]),
         "bani_genome_decode": (C.c_int, [vp, vp, i32, vp, i64]),
@@ -89,6 +91,10 @@ def load_library():
         "bani_index_destroy": (None, [vp]),
         "bani_index_stats": (C.c_int, [vp, P(u64), P(u64), P(u64), P(u64), P(u64)]),
         "bani_index_minimizers": (C.c_int, [vp, vp, vp, u64]),
+        "bani_index_save": (C.c_int, [vp, vp, C.c_char_p]),
+        "bani_index_load": (C.c_int, [vp, C.c_char_p, P(vp)]),
+        "bani_index_contigs": (C.c_int, [vp, vp, u64, vp, u64]),
+        "bani_qsketch_from_index": (C.c_int, [vp, vp, vp, i32, vp, P(vp)]),
         "bani_index_lookup": (C.c_int, [vp, vp, u32, vp, vp, u64, P(u64)]),
         "bani_map_genome": (C.c_int, [vp, vp, vp, P(vp), P(u64), P(u64), P(MapCounters)]),
         "bani_map_cgi": (C.c_int, [vp, vp, P(vp), i32, P(vp), P(u64), vp, P(MapCounters)]),
@@ -114,8 +120,9 @@ EXPORTED_SYMBOLS = [
     "bani_last_error", "bani_version", "bani_params_default", "bani_recommended_window_size", "bani_device_count",
     "bani_stat_min_hits_relaxed", "bani_stat_identity", "bani_ctx_create", "bani_ctx_destroy", "bani_ctx_params",
     "bani_ctx_sync", "bani_ctx_stream", "bani_ctx_launch_count", "bani_ctx_set_flag", "bani_ctx_profile_enable", "bani_ctx_profile_read", "bani_host_alloc", "bani_host_free", "bani_genome_create",
-    "bani_genome_create_batch", "bani_genome_destroy", "bani_genome_info", "bani_genome_decode", "bani_index_build",
-    "bani_index_destroy", "bani_index_stats", "bani_index_minimizers", "bani_index_lookup", "bani_map_genome",
+    "bani_genome_create_batch", "bani_pack_contig", "bani_genome_create_packed_batch", "bani_genome_destroy", "bani_genome_info", "bani_genome_decode", "bani_index_build",
+    "bani_index_destroy", "bani_index_stats", "bani_index_minimizers", "bani_index_save", "bani_index_load", "bani_index_contigs",
+    "bani_qsketch_from_index", "bani_index_lookup", "bani_map_genome",
     "bani_map_cgi", "bani_free", "bani_synth_genome", "bani_qsketch_create", "bani_qsketch_destroy", "bani_qsketch_info",
     "bani_qsketch_export", "bani_qsketch_import", "bani_map_cgi_sketch"]
 
@@ -248,6 +255,16 @@ class Context:
             out.append(Genome(self, C.c_void_p(hs[g]), meta))
         return out
 
+    def genomes_from_packed(self, batch, async_=False):
+        """Host-packed ingest (bani_genome_create_packed_batch): `batch` is a PackedBatch.  async_=True returns at once;
+        the batch's (pinned) arrays must then stay untouched until the genomes have been consumed."""
+        n = len(batch.gen_off) - 1
+        hs = (C.c_void_p * max(n, 1))()
+        _check(self.lib.bani_genome_create_packed_batch(
+            self.h, n, batch.gen_off.ctypes.data, batch.contig_len.ctypes.data, batch.word_off.ctypes.data, batch.words.ctypes.data,
+            batch.exc_off.ctypes.data, batch.exc_pos.ctypes.data, batch.exc_byte.ctypes.data, 1 if async_ else 0, hs))
+        return [Genome(self, C.c_void_p(hs[g]), batch.metas[g]) for g in range(n)]
+
     def pinned(self, nbytes):
         """A pinned uint8 host buffer (numpy view); freed when the returned array's base is collected."""
         p = C.c_void_p()
@@ -261,6 +278,64 @@ class Context:
             out = np.empty(length, np.uint8)
         _check(self.lib.bani_synth_genome(self.h, seed, ancestor, strain, ppm, length, out.ctypes.data))
         return out
+
+
+class PackedBatch:
+    """Genomes 2-bit packed on the HOST (bani_pack_contig; no GPU needed): what a reader thread hands to the upload.
+    list_of_contig_lists[g] = [(name, bytes-like)] or [bytes-like]; alloc(nbytes) -> uint8 array (e.g. Context.pinned)."""
+
+    def __init__(self, list_of_contig_lists, alloc=None, threads=0):
+        lib = load_library()
+        alloc = alloc or (lambda n: np.empty(max(n, 1), np.uint8))
+        contigs, self.metas, gen_off = [], [], [0]
+        for cl in list_of_contig_lists:
+            m = []
+            for c in cl:
+                nm, sq = c if isinstance(c, tuple) else ("", c)
+                a = np.frombuffer(sq, dtype=np.uint8) if not isinstance(sq, np.ndarray) else np.ascontiguousarray(sq, dtype=np.uint8)
+                m.append((nm, len(a)))
+                contigs.append(a)
+            self.metas.append(m)
+            gen_off.append(len(contigs))
+        nc = len(contigs)
+        self.gen_off = np.asarray(gen_off, np.int32)
+        self.contig_len = np.asarray([len(a) for a in contigs] + [0], np.int32)
+        wlen = [((len(a) + 15) // 16 + 3) // 4 * 4 for a in contigs]
+        self.word_off = np.zeros(nc + 1, np.int64)
+        self.word_off[1:] = np.cumsum(wlen)
+        total_words = int(self.word_off[nc])
+        self.words = alloc(4 * (total_words + 8)).view(np.uint32)
+        self.words[:] = 0
+        exc = [None] * nc
+
+        def one(c):
+            a = contigs[c]
+            cap = max(len(a) // 256, 64)
+            while True:
+                ep = np.empty(cap, np.uint32); eb = np.empty(cap, np.uint8); n = C.c_uint64()
+                _check(lib.bani_pack_contig(a.ctypes.data, len(a), self.words[int(self.word_off[c]):].ctypes.data, ep.ctypes.data, eb.ctypes.data, cap, C.byref(n)))
+                if n.value <= cap:
+                    exc[c] = (ep[:n.value], eb[:n.value])
+                    return
+                cap = n.value
+
+        if threads > 1 and nc > 1:
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(threads) as ex:
+                list(ex.map(one, range(nc)))
+        else:
+            for c in range(nc):
+                one(c)
+        self.exc_off = np.zeros(nc + 1, np.int64)
+        if nc:
+            self.exc_off[1:] = np.cumsum([len(e[0]) for e in exc])
+        ne = int(self.exc_off[nc])
+        self.exc_pos = alloc(4 * max(ne, 1)).view(np.uint32)
+        self.exc_byte = alloc(max(ne, 1))
+        for c in range(nc):
+            a, b = int(self.exc_off[c]), int(self.exc_off[c + 1])
+            self.exc_pos[a:b] = exc[c][0]; self.exc_byte[a:b] = exc[c][1]
+        self.h2d_bytes = 4 * total_words + 5 * ne
 
 
 class Genome:
@@ -295,8 +370,11 @@ class Genome:
 class Sketch:
     """skch::Sketch: builds the reference index on construction (winSketch.hpp:109-115)."""
 
-    def __init__(self, ctx, ref_genomes):
+    def __init__(self, ctx, ref_genomes, _handle=None):
         self.ctx = ctx
+        if _handle is not None:
+            self.h, self.refs = _handle, []
+            return
         self.refs = list(ref_genomes)
         arr = (C.c_void_p * max(len(self.refs), 1))(*[g.h for g in self.refs])
         h = C.c_void_p()
@@ -305,6 +383,25 @@ class Sketch:
         # public members of the reference class
         self.metadata = [m for g in self.refs for m in g.metadata]                  # winSketch.hpp:66
         self.sequencesByFileInfo = list(np.cumsum([len(g.metadata) for g in self.refs]).astype(int))   # :75
+
+    def save(self, path):
+        """On-disk sketch cache (bani_index_save): records + contig table + parameters; names are the caller's."""
+        _check(self.ctx.lib.bani_index_save(self.ctx.h, self.h, os.fsencode(path)))
+
+    @classmethod
+    def load(cls, ctx, path, names=None):
+        """bani_index_load on a context with the same k / window / fragLen; metadata lengths come from the file,
+        contig names from `names` (optional list, one per contig)."""
+        h = C.c_void_p()
+        _check(ctx.lib.bani_index_load(ctx.h, os.fsencode(path), C.byref(h)))
+        sk = cls(ctx, None, _handle=h)
+        st = sk.stats()
+        cl = np.zeros(max(st["n_contigs"], 1), np.int32); sbf = np.zeros(max(st["n_genomes"], 1), np.int32)
+        _check(ctx.lib.bani_index_contigs(h, cl.ctypes.data, len(cl), sbf.ctypes.data, len(sbf)))
+        nc = st["n_contigs"]
+        sk.metadata = [((names[c] if names else ""), int(cl[c])) for c in range(nc)]
+        sk.sequencesByFileInfo = [int(x) for x in sbf[:st["n_genomes"]]]
+        return sk
 
     def stats(self):
         a = [C.c_uint64() for _ in range(5)]
@@ -395,6 +492,8 @@ class QuerySketch:
         if _handle is not None:
             self.h = _handle
             return
+        if query_genomes is None:
+            raise ValueError("query genomes, or QuerySketch.from_index / from_device_buffer")
         qs = list(query_genomes)
         arr = (C.c_void_p * max(len(qs), 1))(*[g.h for g in qs])
         ids = None
@@ -405,6 +504,16 @@ class QuerySketch:
         _check(ctx.lib.bani_qsketch_create(ctx.h, arr, len(qs), ids.ctypes.data if ids is not None else None,
                                            hint.h if hint is not None else None, C.byref(h)))
         self.h = h
+
+    @classmethod
+    def from_index(cls, ctx, sketch, genome_ordinals, query_ids=None):
+        """Fragment sketches of genomes OF the index by ordinal, from the index alone (bani_qsketch_from_index)."""
+        ords = np.ascontiguousarray(genome_ordinals, dtype=np.int32)
+        ids = np.ascontiguousarray(query_ids if query_ids is not None else genome_ordinals, dtype=np.int32)
+        assert len(ids) == len(ords)
+        h = C.c_void_p()
+        _check(ctx.lib.bani_qsketch_from_index(ctx.h, sketch.h, ords.ctypes.data, len(ords), ids.ctypes.data, C.byref(h)))
+        return cls(ctx, _handle=h)
 
     @classmethod
     def from_device_buffer(cls, ctx, device_ptr, nbytes):

@@ -96,6 +96,7 @@ int bani_ctx_create(int device, const bani_params *p, bani_ctx **out)
   }
   dev_cache_flush(device);                   // blocks cached under streams of destroyed contexts
   BANI_CUDA(cudaStreamCreateWithFlags(&c->c.stream, cudaStreamNonBlocking));
+  BANI_CUDA(cudaStreamCreateWithFlags(&c->c.copyStream, cudaStreamNonBlocking));
   *out = c.release();
   return BANI_OK;
   BANI_CATCH
@@ -109,8 +110,10 @@ void bani_ctx_destroy(bani_ctx *ctx)
   ctx->c.d_minHits.release(); ctx->c.d_rowOff.release(); ctx->c.d_ident.release(); ctx->c.d_upper.release();
   ctx->c.slots.clear();
   cudaStreamSynchronize(ctx->c.stream);
+  cudaStreamSynchronize(ctx->c.copyStream);
   dev_cache_flush(ctx->c.device);            // blocks are keyed by stream: return them before it dies
   cudaStreamDestroy(ctx->c.stream);
+  cudaStreamDestroy(ctx->c.copyStream);
   delete ctx;
 }
 
@@ -125,6 +128,7 @@ int bani_ctx_sync(bani_ctx *ctx)
   BANI_TRY
   if (!ctx) fail(BANI_ERR_ARG, "null context");
   BANI_CUDA(cudaSetDevice(ctx->c.device));
+  BANI_CUDA(cudaStreamSynchronize(ctx->c.copyStream));
   BANI_CUDA(cudaStreamSynchronize(ctx->c.stream));
   return BANI_OK;
   BANI_CATCH
@@ -140,6 +144,7 @@ int bani_ctx_set_flag(bani_ctx *ctx, const char *name, int64_t value)
   else if (n == "max_hits_per_piece") { if (value < 1) fail(BANI_ERR_ARG, "max_hits_per_piece must be positive"); f.maxHitsPerPiece = value; }
   else if (n == "frag_l1_max") { if (value < 0) fail(BANI_ERR_ARG, "frag_l1_max must not be negative"); f.fragL1Max = value; }
   else if (n == "l2e_buckets") { if (value != 0 && value != 1024 && value != 4096) fail(BANI_ERR_ARG, "l2e_buckets must be 0, 1024 or 4096"); f.l2eBuckets = (int)value; }
+  else if (n == "upload_group_words") { if (value < 1) fail(BANI_ERR_ARG, "upload_group_words must be positive"); f.uploadGroupWords = value; }
   else fail(BANI_ERR_ARG, "unknown flag '%s'", name);
   return BANI_OK;
   BANI_CATCH
@@ -215,6 +220,37 @@ int bani_genome_create_batch(bani_ctx *ctx, int32_t n_genomes, const int32_t *ge
   BANI_CATCH
 }
 
+int bani_pack_contig(const uint8_t *seq, int64_t len, uint32_t *words, uint32_t *exc_pos, uint8_t *exc_byte, uint64_t exc_cap, uint64_t *n_exc)
+{
+  BANI_TRY
+  if (len < 0 || len > 0x7fffffff || (len && (!seq || !words)) || !n_exc || (exc_cap && (!exc_pos || !exc_byte))) fail(BANI_ERR_ARG, "bad argument");
+  *n_exc = host_pack_contig(seq, len, words, exc_pos, exc_byte, exc_cap);
+  return BANI_OK;
+  BANI_CATCH
+}
+
+int bani_genome_create_packed_batch(bani_ctx *ctx, int32_t n_genomes, const int32_t *gen_off, const int32_t *contig_len, const int64_t *word_off,
+                                    const uint32_t *words, const int64_t *exc_off, const uint32_t *exc_pos, const uint8_t *exc_byte,
+                                    int32_t async, bani_genome **out)
+{
+  BANI_TRY
+  if (!ctx || !out || n_genomes < 0 || (n_genomes && (!gen_off || !contig_len || !word_off || !exc_off))) fail(BANI_ERR_ARG, "null argument");
+  BANI_CUDA(cudaSetDevice(ctx->c.device));
+  for (int g = 0; g < n_genomes; g++) if (gen_off[g + 1] < gen_off[g]) fail(BANI_ERR_ARG, "genome offsets must ascend");
+  if (n_genomes) {
+    const int32_t c0 = gen_off[0], c1 = gen_off[n_genomes];
+    bool anyBases = false;
+    for (int32_t c = c0; c < c1; c++) anyBases |= contig_len[c] > 0;
+    if (anyBases && !words) fail(BANI_ERR_ARG, "null packed buffer");
+    if (exc_off[c1] > exc_off[c0] && (!exc_pos || !exc_byte)) fail(BANI_ERR_ARG, "null exception arrays");
+  }
+  std::vector<Genome *> gs(n_genomes, nullptr);
+  genome_create_packed_batch(&ctx->c, n_genomes, gen_off, contig_len, word_off, words, exc_off, exc_pos, exc_byte, async != 0, gs.data());
+  for (int g = 0; g < n_genomes; g++) { bani_genome *h = new bani_genome(); h->g = std::move(*gs[g]); delete gs[g]; out[g] = h; }
+  return BANI_OK;
+  BANI_CATCH
+}
+
 int bani_genome_create(bani_ctx *ctx, int32_t n_contigs, const int64_t *off, const uint8_t *seq, bani_genome **out)
 {
   int32_t go[2] = {0, n_contigs};
@@ -280,6 +316,38 @@ int bani_index_stats(const bani_index *ix, uint64_t *n_minimizers, uint64_t *n_u
   if (n_contigs) *n_contigs = (uint64_t)ix->ix->nContigs;
   if (n_genomes) *n_genomes = (uint64_t)ix->ix->nGenomes;
   return BANI_OK;
+}
+
+int bani_index_save(bani_ctx *ctx, const bani_index *ix, const char *path)
+{
+  BANI_TRY
+  if (!ctx || !ix || !ix->ix || !path) fail(BANI_ERR_ARG, "null argument");
+  BANI_CUDA(cudaSetDevice(ctx->c.device));
+  index_save(&ctx->c, ix->ix, path);
+  return BANI_OK;
+  BANI_CATCH
+}
+
+int bani_index_load(bani_ctx *ctx, const char *path, bani_index **out)
+{
+  BANI_TRY
+  if (!ctx || !path || !out) fail(BANI_ERR_ARG, "null argument");
+  BANI_CUDA(cudaSetDevice(ctx->c.device));
+  Index *ix = index_load(&ctx->c, path);
+  bani_index *h = new bani_index(); h->ix = ix; *out = h;
+  return BANI_OK;
+  BANI_CATCH
+}
+
+int bani_index_contigs(const bani_index *ix, int32_t *contig_len, uint64_t cap_contigs, int32_t *seqs_by_file, uint64_t cap_genomes)
+{
+  BANI_TRY
+  if (!ix || !ix->ix) fail(BANI_ERR_ARG, "null index");
+  const Index *x = ix->ix;
+  if (contig_len) { if (cap_contigs < x->contigLen.size()) fail(BANI_ERR_ARG, "contig buffer too small"); memcpy(contig_len, x->contigLen.data(), 4 * x->contigLen.size()); }
+  if (seqs_by_file) { if (cap_genomes < x->seqsByFile.size()) fail(BANI_ERR_ARG, "genome buffer too small"); memcpy(seqs_by_file, x->seqsByFile.data(), 4 * x->seqsByFile.size()); }
+  return BANI_OK;
+  BANI_CATCH
 }
 
 int bani_index_minimizers(bani_ctx *ctx, const bani_index *ixh, bani_minimizer *out, uint64_t cap)
@@ -390,6 +458,19 @@ int bani_qsketch_create(bani_ctx *ctx, bani_genome *const *queries, int32_t n_qu
   for (int i = 0; i < n_queries; i++) { if (!queries[i]) fail(BANI_ERR_ARG, "null genome handle"); qs[i] = &queries[i]->g; }
   std::unique_ptr<bani_qsketch> h(new bani_qsketch());
   h->qs = qsketch_create(&ctx->c, qs.data(), n_queries, query_ids, hint ? hint->ix : nullptr);
+  *out = h.release();
+  return BANI_OK;
+  BANI_CATCH
+}
+
+int bani_qsketch_from_index(bani_ctx *ctx, const bani_index *ix, const int32_t *genome_ordinals, int32_t n_queries,
+                            const int32_t *query_ids, bani_qsketch **out)
+{
+  BANI_TRY
+  if (!ctx || !ix || !ix->ix || n_queries < 0 || (n_queries && !genome_ordinals) || !out) fail(BANI_ERR_ARG, "null argument");
+  BANI_CUDA(cudaSetDevice(ctx->c.device));
+  std::unique_ptr<bani_qsketch> h(new bani_qsketch());
+  h->qs = qsketch_from_index(&ctx->c, ix->ix, genome_ordinals, n_queries, query_ids);
   *out = h.release();
   return BANI_OK;
   BANI_CATCH

@@ -90,6 +90,15 @@ struct SeqDesc {
 
 uint64_t next_genome_uid();
 
+// Device block shared by the genomes of one upload sub-batch of the host-packed path (bani_genome_create_packed_batch):
+// one H2D copy per array on the context's copy stream; `ready` is recorded behind them and every consumer makes its
+// stream wait for it, so uploads of later sub-batches overlap the sketch launches of earlier ones.
+struct GenomeBlock {
+  DevBuf<uint32_t> words; DevBuf<uint32_t> excPos; DevBuf<uint8_t> excByte;
+  cudaEvent_t ready = nullptr; int device = 0;
+  ~GenomeBlock() { if (ready) { cudaSetDevice(device); cudaEventDestroy(ready); } }
+};
+
 struct Genome {
   uint64_t uid = next_genome_uid();  // identity that survives address reuse (index membership, see Index::members)
   int device = 0;
@@ -98,9 +107,15 @@ struct Genome {
   std::vector<int64_t> wordOff;      // per contig, into packed (multiple of 4 words)
   std::vector<int64_t> excOff;       // per contig +1, into exc arrays
   uint64_t totalLen = 0, nExc = 0;
-  DevBuf<uint32_t> packed;
+  DevBuf<uint32_t> packed;           // own buffers (ASCII ingest, pack.cu) ...
   DevBuf<uint32_t> excPos;
   DevBuf<uint8_t>  excByte;
+  std::shared_ptr<GenomeBlock> blk;  // ... or a slice of a shared upload block (host-packed ingest)
+  const uint32_t *blkWords = nullptr; const uint32_t *blkExcPos = nullptr; const uint8_t *blkExcByte = nullptr;
+  const uint32_t *packedBase() const { return blk ? blkWords : packed.p; }
+  const uint32_t *excPosBase() const { return blk ? blkExcPos : excPos.p; }
+  const uint8_t  *excByteBase() const { return blk ? blkExcByte : excByte.p; }
+  void wait_ready(cudaStream_t st) const { if (blk && blk->ready) cudaStreamWaitEvent(st, blk->ready, 0); }
 };
 
 struct Ctx;
@@ -135,6 +150,9 @@ struct Index {
   int dirBits = 0;
   // position-ordered records (== Sketch::minimizerIndex as SoA) + same-hash links
   DevBuf<uint32_t> hash; DevBuf<int32_t> wpos; DevBuf<int32_t> seqId; DevBuf<uint32_t> link;
+  DevBuf<int2> pos8;                 // {wpos, seqId} per record: what the L1 stage fetches per sorted hit (one 8-byte load)
+  DevBuf<uint2> rec8;                // 8-byte L2 record: x = hash, y = back:14 | fwd:14 | tie | new | gone (index.cu); valid where blkMax allows
+  DevBuf<uint32_t> blkMax;           // per 1024 records: max back | max fwd << 16 (0xFFFF: a link does not fit 14 bits)
   DevBuf<uint4> rec;                 // 16-byte L2 record: x=hash, y=wpos|tie<<31, z=twin link, w=back|fwd<<16 (index.cu)
   int cmw = 0;                       // super-window width the back/fwd fields were computed for
   int k = 0, w = 0, fragLen = 0;     // parameters of the context the index was built with
@@ -146,6 +164,10 @@ struct Index {
   DevBuf<uint32_t> uoff;             // U+1 offsets into posIdx
   DevBuf<uint32_t> posIdx;           // M record indices, sorted by (hash, record index)
   DevBuf<uint32_t> dir;              // (1<<dirBits)+1 bucket directory over the top bits of the hash
+  // one-sector probe table: 2^tabBits buckets of 4 entries {x = (hash & ~0xFF) | min(count, 255), y = offset into posIdx},
+  // bucket = LOW bits of the hash (uniform, unlike the top bits of a minimizer hash); x == 0 = empty.  A full bucket or a
+  // saturated count sends the probe to the sorted keys above (index.cu: table_fill_kernel, map.cu: lookup_kernel)
+  DevBuf<uint2> tab; int tabBits = 0;
   std::vector<int32_t> contigLen;    // host copies
   std::vector<int32_t> seqsByFile;   // cumulative contig count per genome (sequencesByFileInfo)
   // Which genomes the index was built from (uid -> first contig ordinal) and, per hashed position, whether it was
@@ -172,11 +194,13 @@ struct CtxFlags {
   long long maxHitsPerPiece = 3ll << 29;      // a piece that gathers more index hits is split at a query boundary
   long long fragL1Max = 8192;                 // hits per fragment handled inside one CTA (<= FRAG_L1_MAX)
   int l2eBuckets = 0;                         // 0 = adaptive; 1024 / 4096 force the size of the L2 rank directory
+  long long uploadGroupWords = 16ll << 20;    // packed words (16 bases each) per upload group of the host-packed ingest
 };
 
 struct Ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copyStream = nullptr;   // H2D uploads of host-packed genomes (overlap with the sketch launches on `stream`)
   bani_params prm{};
   CtxFlags flags;
   int smCount = 0;
@@ -234,17 +258,25 @@ struct Stage {
 void genome_create_batch(Ctx *ctx, int32_t nGenomes, const int32_t *genOff, const int64_t *off,
                          const uint8_t *seq, Genome **out);
 void genome_decode(Ctx *ctx, const Genome *g, int32_t contig, uint8_t *out, int64_t cap);
+void genome_create_packed_batch(Ctx *ctx, int32_t nGenomes, const int32_t *genOff, const int32_t *contigLen, const int64_t *wordOff,
+                                const uint32_t *words, const int64_t *excOff, const uint32_t *excPos, const uint8_t *excByte,
+                                bool async, Genome **out);
+uint64_t host_pack_contig(const uint8_t *seq, int64_t len, uint32_t *words, uint32_t *excPos, uint8_t *excByte, uint64_t excCap);
 
 // sketch.cu : windowed minimizers of a list of sequences, records compacted in
 // (sequence, wpos) order.  Outputs may be null (skipped).  Returns total records
 // (which may exceed `cap`; only the first cap are stored).
+// recBase: records already written by earlier launches into the same output arrays (index build in upload groups);
+// outputs and segStart values are offset by it, `cap` is the capacity of the whole arrays.
 uint64_t sketch_sequences(Ctx *ctx, const SeqDesc *d_desc, int32_t nSeq, const int32_t *h_len, int32_t uniformLen,
                           uint32_t *o_hash, int32_t *o_wpos, int32_t *o_seqId, uint64_t cap,
                           uint32_t *o_segStart /* nSeq+1 */,
-                          uint32_t *o_validBits = nullptr, const unsigned long long *bitBase = nullptr);
+                          uint32_t *o_validBits = nullptr, const unsigned long long *bitBase = nullptr, uint64_t recBase = 0);
 
 // index.cu
 Index *index_build(Ctx *ctx, Genome *const *refs, int32_t nRefs);
+void   index_save(Ctx *ctx, const Index *ix, const char *path);
+Index *index_load(Ctx *ctx, const char *path);
 
 // map.cu
 struct MapOutput {
@@ -256,6 +288,7 @@ struct MapOutput {
 void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_t nq,
                  bool wantRows, bool wantCgi, MapOutput &out);
 QSketch *qsketch_create(Ctx *ctx, const Genome *const *queries, int32_t nq, const int32_t *queryIds, const Index *hint);
+QSketch *qsketch_from_index(Ctx *ctx, const Index *ix, const int32_t *ordinals, int32_t nq, const int32_t *queryIds);
 uint64_t qsketch_export_bytes(const QSketch *qs);
 void qsketch_export(Ctx *ctx, const QSketch *qs, void *devBuf, uint64_t cap);
 QSketch *qsketch_import(Ctx *ctx, const void *devBuf, uint64_t bytes);
@@ -272,7 +305,7 @@ __host__ __device__ inline int frag_class_items(int cls)
 struct FragL1Args {
   const uint32_t *segStart; const int32_t *sCount; int32_t F;
   const uint32_t *hitLo, *hitCnt; const unsigned long long *hitOff;
-  const uint32_t *posIdx; const int32_t *recSeq, *recWpos;
+  const uint32_t *posIdx; const int2 *recPos;    // recPos[r] = {wpos, seqId} of record r
   const int32_t *minHits; int fragLen, keyBits;
   int32_t *stSeq, *stStart, *stEnd;      // staging, addressed by global hit offset
   uint32_t *candCount;                   // per fragment

@@ -40,28 +40,30 @@ __global__ void frag_classify_kernel(const uint32_t *segStart, const unsigned lo
   if (cls <= FRAG_NCLASS) { const uint32_t o = atomicAdd(&classCount[cls], 1u); if (cls < FRAG_NCLASS) classList[(size_t)cls * F + o] = (uint32_t)f; }
 }
 
-// Block-wide stable LSD radix sort of CAP = 256 * ITEMS 32-bit keys held in shared memory, 8 bits per pass.
+// Block-wide stable LSD radix sort of CAP = 256 * ITEMS 32-bit keys held in shared memory, DB bits per pass (8 for the
+// small classes, 10 for the others: a 29-bit record index takes 3 passes instead of 4).
 // Warp w owns the keys [w * 32 * ITEMS, (w+1) * 32 * ITEMS) of the current order and ranks them round by round
 // (32 consecutive keys per round): lanes with the same digit find each other with match.any, the lowest of them
 // bumps the warp's digit counter once for the whole group, the others take their place from the lane order --
-// which keeps equal digits in input order, the property LSD needs.  Then one thread per digit turns the per-warp
-// counts into offsets (prefix over warps, block scan over digits) and the keys are scattered to the other buffer.
-// Returns the buffer that holds the sorted keys.
-template <int ITEMS>
-__device__ __forceinline__ uint32_t *block_radix_sort(uint32_t *in, uint32_t *out, uint16_t *hist /* [8][256] */,
-                                                       uint32_t *digitBase /* [256] */, uint32_t *wsum /* [8] */, int keyBits)
+// which keeps equal digits in input order, the property LSD needs.  Then every thread turns the per-warp counts of
+// its 2^DB / 256 consecutive digits into offsets (prefix over warps, block scan over digits) and the keys are scattered
+// to the other buffer.  Returns the buffer that holds the sorted keys.
+template <int ITEMS, int DB>
+__device__ __forceinline__ uint32_t *block_radix_sort(uint32_t *in, uint32_t *out, uint16_t *hist /* [8][2^DB] */,
+                                                       uint32_t *digitBase /* [2^DB] */, uint32_t *wsum /* [8] */, int keyBits)
 {
+  constexpr int ND = 1 << DB, DPT = ND / 256;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const uint32_t ltMask = (1u << lane) - 1u;
-  for (int shift = 0; shift < keyBits; shift += 8) {
-    for (int i = tid; i < 8 * 256 / 2; i += 256) reinterpret_cast<uint32_t *>(hist)[i] = 0;
+  for (int shift = 0; shift < keyBits; shift += DB) {
+    for (int i = tid; i < 8 * ND / 2; i += 256) reinterpret_cast<uint32_t *>(hist)[i] = 0;
     __syncthreads();
     uint32_t key[ITEMS]; uint32_t lr[ITEMS];
-    uint16_t *myHist = hist + w * 256;
+    uint16_t *myHist = hist + w * ND;
 #pragma unroll
     for (int r = 0; r < ITEMS; r++) {
       key[r] = in[w * 32 * ITEMS + r * 32 + lane];
-      const uint32_t d = (key[r] >> shift) & 255u;
+      const uint32_t d = (key[r] >> shift) & (uint32_t)(ND - 1);
       const uint32_t m = __match_any_sync(0xffffffffu, d);
       const int leader = __ffs(m) - 1;
       uint32_t old = 0;
@@ -72,23 +74,30 @@ __device__ __forceinline__ uint32_t *block_radix_sort(uint32_t *in, uint32_t *ou
     }
     __syncthreads();
     {
-      // thread = digit: counts of the 8 warps -> exclusive prefix over warps; total -> exclusive scan over digits
-      uint32_t acc = 0;
+      // thread = DPT consecutive digits: counts of the 8 warps -> exclusive prefix over warps; totals -> exclusive scan over digits
+      uint32_t tot[DPT], sum = 0;
 #pragma unroll
-      for (int ww = 0; ww < 8; ww++) { const uint32_t c = hist[ww * 256 + tid]; hist[ww * 256 + tid] = (uint16_t)acc; acc += c; }
-      uint32_t incl = acc;
+      for (int j = 0; j < DPT; j++) {
+        const int d = tid * DPT + j;
+        uint32_t acc = 0;
+#pragma unroll
+        for (int ww = 0; ww < 8; ww++) { const uint32_t c = hist[ww * ND + d]; hist[ww * ND + d] = (uint16_t)acc; acc += c; }
+        tot[j] = acc; sum += acc;
+      }
+      uint32_t incl = sum;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
       if (lane == 31) wsum[w] = incl;
       __syncthreads();
-      uint32_t base = incl - acc;
+      uint32_t base = incl - sum;
       for (int ww = 0; ww < w; ww++) base += wsum[ww];
-      digitBase[tid] = base;
+#pragma unroll
+      for (int j = 0; j < DPT; j++) { digitBase[tid * DPT + j] = base; base += tot[j]; }
     }
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < ITEMS; r++) {
-      const uint32_t d = (key[r] >> shift) & 255u;
+      const uint32_t d = (key[r] >> shift) & (uint32_t)(ND - 1);
       out[digitBase[d] + myHist[d] + lr[r]] = key[r];
     }
     __syncthreads();
@@ -97,17 +106,20 @@ __device__ __forceinline__ uint32_t *block_radix_sort(uint32_t *in, uint32_t *ou
   return in;
 }
 
+template <int ITEMS> struct FragSortBits { static constexpr int DB = ITEMS >= 3 ? 10 : 8; };
+
 template <int ITEMS>
 __global__ void __launch_bounds__(256)
 frag_l1_kernel(const FragL1Args a, const uint32_t *list, uint32_t count)
 {
   constexpr int CAP = 256 * ITEMS;
+  constexpr int DB = FragSortBits<ITEMS>::DB, ND = 1 << DB;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint32_t *bufA = reinterpret_cast<uint32_t *>(smem_raw);                  // CAP
   uint32_t *bufB = bufA + CAP;                                              // CAP
-  uint16_t *hist = reinterpret_cast<uint16_t *>(bufB + CAP);                // 8 * 256
-  uint32_t *digitBase = reinterpret_cast<uint32_t *>(hist + 8 * 256);       // 256
-  uint32_t *wsum = digitBase + 256;                                         // 8
+  uint16_t *hist = reinterpret_cast<uint16_t *>(bufB + CAP);                // 8 * ND
+  uint32_t *digitBase = reinterpret_cast<uint32_t *>(hist + 8 * ND);        // ND
+  uint32_t *wsum = digitBase + ND;                                          // 8
   if (blockIdx.x >= count) return;
   const int f = (int)list[blockIdx.x], tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const uint32_t t0 = a.segStart[f];
@@ -139,8 +151,8 @@ frag_l1_kernel(const FragL1Args a, const uint32_t *list, uint32_t count)
   for (int i = n + tid; i < CAP; i += 256) bufA[i] = 0xFFFFFFFFu;
   __syncthreads();
   // ---- 2: sort by record index
-  const uint32_t *sorted = block_radix_sort<ITEMS>(bufA, bufB, hist, digitBase, wsum, a.keyBits);
-  // ---- 3: (seqId, wpos) of the sorted hits; rank r = i*256 + tid (neighbouring lanes = neighbouring records)
+  const uint32_t *sorted = block_radix_sort<ITEMS, DB>(bufA, bufB, hist, digitBase, wsum, a.keyBits);
+  // ---- 3: (wpos, seqId) of the sorted hits, one 8-byte load each; rank r = i*256 + tid (neighbouring lanes = neighbouring records)
   uint32_t keys[ITEMS];
 #pragma unroll
   for (int i = 0; i < ITEMS; i++) keys[i] = sorted[i * 256 + tid];
@@ -149,36 +161,44 @@ frag_l1_kernel(const FragL1Args a, const uint32_t *list, uint32_t count)
 #pragma unroll
   for (int i = 0; i < ITEMS; i++) {
     const int r = i * 256 + tid;
-    if (r < n) { s_w[r] = __ldg(&a.recWpos[keys[i]]); s_seq[r] = __ldg(&a.recSeq[keys[i]]); }
+    if (r < n) { const int2 p = __ldg(&a.recPos[keys[i]]); s_w[r] = p.x; s_seq[r] = p.y; }
   }
   __syncthreads();
   // ---- 4: L1 flags.  Item i of lane `lane` in warp `wid` is rank i*256 + wid*32 + lane: consecutive lanes read
-  //         consecutive words (no bank conflicts), and a ballot gives the head flags of 32 consecutive ranks in order
+  //         consecutive words (no bank conflicts).  Pass 1: does hit r open a raw region (:324-336)?  One evaluation per
+  //         hit; a ballot packs the answers of 32 consecutive ranks into one word of qualW.  Pass 2: head / tail of the
+  //         merged regions from the neighbours' answers (:342-350).
   const int mh = a.minHits[s];
-  auto qual = [&](int i, int32_t &start) -> bool {
-    const int rb = i + mh - 1;
-    if (rb >= n) return false;
-    if (s_seq[rb] != s_seq[i]) return false;
-    const int32_t wb = s_w[rb];
-    if (wb - s_w[i] >= a.fragLen) return false;
-    start = max(0, wb - a.fragLen + 1);
-    return true;
-  };
+  uint32_t *qualW = reinterpret_cast<uint32_t *>(hist);              // [ITEMS][8] words, rank r -> word r >> 5
+  uint16_t *slice = reinterpret_cast<uint16_t *>(qualW + ITEMS * 8); // [ITEMS][8] head counts per 32 consecutive ranks
+  int32_t starts[ITEMS];
+  uint32_t qualMask = 0;
+#pragma unroll
+  for (int i = 0; i < ITEMS; i++) {
+    const int r = i * 256 + tid, rb = r + mh - 1;
+    bool q = false;
+    starts[i] = 0;
+    if (rb < n && s_seq[rb] == s_seq[r]) {
+      const int32_t wb = s_w[rb];
+      if (wb - s_w[r] < a.fragLen) { q = true; starts[i] = max(0, wb - a.fragLen + 1); }
+    }
+    const uint32_t bal = __ballot_sync(0xffffffffu, q);
+    if (lane == 0) qualW[i * 8 + wid] = bal;
+    if (q) qualMask |= 1u << i;
+  }
+  __syncthreads();
+  auto qual_at = [&](int r) -> bool { return (qualW[r >> 5] >> (r & 31)) & 1u; };
+  auto start_at = [&](int r) -> int32_t { return max(0, s_w[r + mh - 1] - a.fragLen + 1); };
   uint32_t headMask = 0, tailMask = 0;           // bit i: item i of this thread
   uint32_t headBallot[ITEMS];                    // heads of the 32 ranks of this warp's slice of item i
-  int32_t starts[ITEMS];
-  uint16_t *slice = hist;                        // [ITEMS][8] head counts per (item, warp) = per 32 consecutive ranks
 #pragma unroll
   for (int i = 0; i < ITEMS; i++) {
     const int r = i * 256 + tid;
-    int32_t st = 0;
-    starts[i] = 0;
     bool hd = false;
-    if (r < n && qual(r, st)) {
-      starts[i] = st;
-      int32_t sp, sn;
-      const bool merged = r > 0 && s_seq[r - 1] == s_seq[r] && qual(r - 1, sp) && s_w[r - 1] >= st;
-      const bool nextMerges = r + 1 < n && s_seq[r + 1] == s_seq[r] && qual(r + 1, sn) && s_w[r] >= sn;
+    if ((qualMask >> i) & 1u) {
+      const int32_t st = starts[i];
+      const bool merged = r > 0 && s_seq[r - 1] == s_seq[r] && qual_at(r - 1) && s_w[r - 1] >= st;
+      const bool nextMerges = r + 1 < n && s_seq[r + 1] == s_seq[r] && qual_at(r + 1) && s_w[r] >= start_at(r + 1);
       hd = !merged;
       if (hd) headMask |= 1u << i;
       if (!nextMerges) tailMask |= 1u << i;
@@ -212,7 +232,8 @@ template <int ITEMS>
 static void launch_class(Ctx *ctx, const FragL1Args &a, const uint32_t *list, uint32_t count, cudaStream_t st)
 {
   if (count == 0) return;
-  const size_t shm = sizeof(uint32_t) * 2 * 256 * ITEMS + 2 * 8 * 256 + 4 * 256 + 64;
+  constexpr int ND = 1 << FragSortBits<ITEMS>::DB;
+  const size_t shm = sizeof(uint32_t) * 2 * 256 * ITEMS + 2 * 8 * ND + 4 * ND + 64;
   if (ctx->first_time((const void *)frag_l1_kernel<ITEMS>))
     BANI_CUDA(cudaFuncSetAttribute(frag_l1_kernel<ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
   frag_l1_kernel<ITEMS><<<count, 256, shm, st>>>(a, list, count);

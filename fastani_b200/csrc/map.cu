@@ -93,21 +93,35 @@ __device__ __forceinline__ int seg_of(const uint32_t *segStart, int F, uint32_t 
   return lo;
 }
 
-__global__ void lookup_kernel(const uint32_t *fragHash, const uint32_t *segStart, const int32_t *sCount, int32_t F,
-                              uint32_t T, const uint32_t *ukeys, const uint32_t *uoff, const uint32_t *dir, int dirBits,
+// Thread per query hash.  One 32-byte sector of the probe table answers almost every probe (hit or miss): bucket = low
+// bits of the hash, 4 entries {x = (hash & ~0xFF) | min(count, 255), y = offset}.  Only a full bucket without a match, or a
+// saturated count, walks the sorted keys (bucket directory over the top bits, then a short binary search).
+__global__ void lookup_kernel(const uint32_t *fragHash, uint32_t T, const uint2 *tab, uint32_t tabMask,
+                              const uint32_t *ukeys, const uint32_t *uoff, const uint32_t *dir, int dirBits,
                               uint32_t *hitLo, uint32_t *hitCnt)
 {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t > T) return;
   if (t == T) { hitCnt[t] = 0; hitLo[t] = 0; return; }
-  const int f = seg_of(segStart, F, t);
+  const uint32_t h = __ldg(&fragHash[t]);
+  const uint4 *bp = reinterpret_cast<const uint4 *>(tab) + 2 * (size_t)(h & tabMask);
+  const uint4 e0 = __ldg(bp), e1 = __ldg(bp + 1);
+  const uint32_t key = h & 0xFFFFFF00u;
+  const uint32_t ex[4] = {e0.x, e0.z, e1.x, e1.z}, ey[4] = {e0.y, e0.w, e1.y, e1.w};
   uint32_t cnt = 0, lo0 = 0;
-  if ((int)(t - segStart[f]) < sCount[f]) {
-    const uint32_t h = fragHash[t];
+  bool full = true, found = false;
+#pragma unroll
+  for (int sl = 0; sl < 4; sl++) {
+    if (ex[sl] == 0u) full = false;
+    else if ((ex[sl] & 0xFFFFFF00u) == key) { found = true; cnt = ex[sl] & 0xFFu; lo0 = ey[sl]; }
+  }
+  if ((found && cnt == 255u) || (!found && full)) {
+    cnt = 0; lo0 = 0;
     const uint32_t b = h >> (32 - dirBits);
     uint32_t lo = dir[b], hi = dir[b + 1];
+    const uint32_t end = hi;
     while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (ukeys[mid] < h) lo = mid + 1; else hi = mid; }
-    if (lo < dir[b + 1] && ukeys[lo] == h) { lo0 = uoff[lo]; cnt = uoff[lo + 1] - lo0; }
+    if (lo < end && ukeys[lo] == h) { lo0 = uoff[lo]; cnt = uoff[lo + 1] - lo0; }
   }
   hitLo[t] = lo0; hitCnt[t] = cnt;
 }
@@ -309,13 +323,19 @@ static constexpr int L2_SHM_BUDGET = 200 * 1024;      // dynamic shared memory g
 static constexpr uint32_t EV_M = 1u, EV_D = 2u, EV_S = 4u, EV_JMASK = 0xFFE0u;
 __host__ __device__ __forceinline__ uint32_t ev_rank(uint32_t j) { return j << 5; }
 
+static constexpr int L2E_RING = 2048;             // events staged per warp of l2_events_kernel (4 KB)
+static constexpr int L2E_FLUSH_IT = 8;            // iterations of 32 records between two flushes = 32 steps of 16 events, one per lane
+static constexpr int L2E_BF_MAX = L2E_RING - 64 * L2E_FLUSH_IT - 96;   // 1440: largest (max back + max fwd) of a staged candidate
+
 struct L2PArgs {
   const int32_t *cFrag, *cSeq, *cStart, *cEnd; uint32_t C;
   const uint32_t *fragCandOff;
   const uint32_t *fragHash; const uint32_t *segStart; const int32_t *sCount;
   const uint4 *rec; const int32_t *recWposSoA; const uint32_t *contigRecOff;
+  const uint2 *rec8; const uint32_t *recLink; const uint32_t *blkMax;      // compact L2 records + per-1024-record link bounds (index.cu)
   int fragLen, cmw, sLimit, shiftA, nBuckets;      // nBuckets: 1024 or 4096 (power of two), directory over h >> shiftA
   uint32_t *cB0, *cE0, *cLast, *cNEv, *cChunks;   // per candidate
+  uint16_t *cMB;                                   // per candidate: bound on `back` of its records when its events can be staged, else 0xFFFF
   const uint32_t *cOff;                            // first 32-byte slot of the candidate's stream; step k is slot cOff + 32 * k
   const unsigned long long *grpOff;                // per warp group of 32 sorted candidates: first step row
   uint16_t *events;
@@ -361,6 +381,16 @@ __global__ void l2_bounds_kernel(const L2PArgs a)
     }
     a.cB0[c] = b0; a.cE0[c] = e0; a.cLast[c] = last;
     const bool fast = s >= 1 && s <= a.sLimit && nEv < (1u << 20);
+    {
+      // can l2_events_kernel stage this candidate's events in its shared-memory ring?  The ring has to span the event
+      // positions still open between two flushes: bounded by the largest `back` plus the largest `fwd` of the records
+      uint32_t mbk = 0, mfw = 0;
+      if (fast && nEv) {
+        const uint32_t blk1 = (last - 1) >> 10;
+        for (uint32_t blk = b0 >> 10; blk <= blk1 && mbk != 0xFFFFu; blk++) { const uint32_t v = __ldg(&a.blkMax[blk]); mbk = max(mbk, v & 0xFFFFu); mfw = max(mfw, v >> 16); }
+      }
+      a.cMB[c] = (uint16_t)((mbk + mfw <= (uint32_t)L2E_BF_MAX) ? mbk : 0xFFFFu);
+    }
     a.cNEv[c] = fast ? nEv : 0u;
     a.cChunks[c] = fast ? (nEv + 15) >> 4 : 0u;      // 32-byte steps of 16 events
     a.cBest[c] = (fast || nEv == 0) ? 0 : -1;   // -1: exact slow kernel
@@ -394,7 +424,6 @@ __global__ void l2_stream_base_kernel(const uint32_t *perm, const unsigned long 
 // event e of a stream that starts at 32-byte slot `base`: 16 events per slot, consecutive steps 32 slots apart
 __device__ __forceinline__ size_t ev_index(uint32_t base, uint32_t e) { return ((size_t)base + (size_t)(e >> 4) * 32) * 16 + (e & 15u); }
 
-static constexpr int L2E_THREADS = 256;
 static constexpr int L2E_BUCKETS = 4096;         // largest directory over h >> shiftA (clamped): ~1 query hash per bucket near 0;
                                                  // shards that see few candidates per fragment use 1024 (cheaper to build)
 
@@ -408,53 +437,130 @@ static constexpr int L2E_BUCKETS = 4096;         // largest directory over h >> 
 //            ahead; a scoring point follows unless another record enters in the same step (tie)
 // (positions: the first window's records occupy 0 .. nInit-1 because for them back >= rb, i.e. mb = rb; afterwards
 //  "enters" and "leaves" interleave by time, leaves first on ties -- the merge of computeMap.hpp:455-492.)
-__global__ void __launch_bounds__(L2E_THREADS)
+//
+// CTA per fragment (NT threads: 256, 128 or 64 -- shards that see few candidates per fragment use small CTAs so that no
+// warp idles), warp per candidate, lane per record.  Two ways to write the 16-bit codes:
+//   staged  (cMB != 0xFFFF) the 8-byte compact records are read (hash | back:14 fwd:14 tie new gone); the codes go to a
+//           per-warp ring in shared memory and leave it as whole 32-byte steps, one coalesced sector per lane: after the
+//           records up to rb every position below 2*(rb+1) - max(back) is final, and between two flushes the open
+//           positions span at most max(back) + max(fwd) + 64 * L2E_FLUSH_IT + 80 events (l2_bounds_kernel checks that
+//           against the ring with the per-block bounds of the index)
+//   direct  (low-complexity stretches with very long windows) 16-byte records, two 2-byte global stores per record
+template <int NT>
+__global__ void __launch_bounds__(NT)
 l2_events_kernel(const L2PArgs a)
 {
   extern __shared__ __align__(16) uint32_t smem[];
-  __shared__ uint32_t s_wsum[L2E_THREADS / 32];
+  __shared__ uint32_t s_wsum[NT / 32];
+  constexpr int NW = NT / 32;
   const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const uint32_t c0 = a.fragCandOff[f], c1 = a.fragCandOff[f + 1];
   if (c0 == c1) return;
   const int s = a.sCount[f];
   if (s < 1 || s > a.sLimit) return;
-  uint32_t *Q = smem;                                          // s hashes + 3 sentinels
-  uint32_t *tab = smem + a.sLimit + 4;                         // L2E_BUCKETS + 1: bucket -> first rank
-  uint2 *QP = reinterpret_cast<uint2 *>(smem + ((a.sLimit + 4 + L2E_BUCKETS + 4 + 1) & ~1));   // {Q[j], Q[j+1]}: both probes in one load
+  uint16_t *ring = reinterpret_cast<uint16_t *>(smem) + wid * L2E_RING;                 // NW rings first (16-byte aligned)
+  uint32_t *Q = smem + NW * (L2E_RING / 2);                                             // s hashes + 3 sentinels
+  uint32_t *tab = Q + a.sLimit + 4;                                                     // L2E_BUCKETS + 1: bucket -> first rank
+  uint2 *QP = reinterpret_cast<uint2 *>(smem + ((NW * (L2E_RING / 2) + a.sLimit + 4 + L2E_BUCKETS + 4 + 1) & ~1));   // {Q[j], Q[j+1]}: both probes in one load
+  const int NB = a.nBuckets;
   {
     const uint32_t *Qg = a.fragHash + a.segStart[f];
-    for (int i = tid; i < s + 3; i += L2E_THREADS) Q[i] = i < s ? Qg[i] : 0xFFFFFFFFu;
-    for (int i = tid; i < s + 2; i += L2E_THREADS) QP[i] = make_uint2(i < s ? Qg[i] : 0xFFFFFFFFu, i + 1 < s ? Qg[i + 1] : 0xFFFFFFFFu);
-    const int NB = a.nBuckets;
-    for (int i = tid; i <= NB; i += L2E_THREADS) tab[i] = 0;
+    for (int i = tid; i < s + 3; i += NT) Q[i] = i < s ? Qg[i] : 0xFFFFFFFFu;
+    for (int i = tid; i < s + 2; i += NT) QP[i] = make_uint2(i < s ? Qg[i] : 0xFFFFFFFFu, i + 1 < s ? Qg[i + 1] : 0xFFFFFFFFu);
+    for (int i = tid; i <= NB; i += NT) tab[i] = 0;
     __syncthreads();
-    for (int i = tid; i < s; i += L2E_THREADS) atomicAdd(&tab[min(Q[i] >> a.shiftA, (uint32_t)(NB - 1))], 1u);
+    for (int i = tid; i < s; i += NT) atomicAdd(&tab[min(Q[i] >> a.shiftA, (uint32_t)(NB - 1))], 1u);
     __syncthreads();
-    // exclusive prefix over the bucket counts: NB / 256 consecutive buckets per thread
-    constexpr int PERMAX = L2E_BUCKETS / L2E_THREADS;
-    const int PER = NB / L2E_THREADS;
-    uint32_t cnt[PERMAX], sum = 0;
+    // exclusive prefix over the bucket counts: every warp owns NB / NW consecutive buckets and walks them 32 at a time
+    // (conflict-free reads, shuffle scan, running carry); pass 1 gives the warp totals, pass 2 writes the prefixes
+    const int chunk = NB / NW, cbeg = wid * chunk;
+    uint32_t wt = 0;
+    for (int i = lane; i < chunk; i += 32) wt += tab[cbeg + i];
 #pragma unroll
-    for (int i = 0; i < PERMAX; i++) { cnt[i] = i < PER ? tab[tid * PER + i] : 0u; sum += cnt[i]; }
-    uint32_t incl = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-    if (lane == 31) s_wsum[wid] = incl;
+    for (int o = 16; o; o >>= 1) wt += __shfl_xor_sync(0xffffffffu, wt, o);
+    if (lane == 0) s_wsum[wid] = wt;
     __syncthreads();
-    uint32_t run = incl - sum;
-    for (int i = 0; i < wid; i++) run += s_wsum[i];
+    uint32_t carry = 0;
+    for (int i = 0; i < wid; i++) carry += s_wsum[i];
+    for (int i = lane; i < chunk; i += 32) {
+      const uint32_t cnt = tab[cbeg + i];
+      uint32_t incl = cnt;
 #pragma unroll
-    for (int i = 0; i < PERMAX; i++) if (i < PER) { tab[tid * PER + i] = run; run += cnt[i]; }
-    if (tid == L2E_THREADS - 1) tab[NB] = run;
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+      tab[cbeg + i] = carry + incl - cnt;
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (tid == NT - 1) tab[NB] = carry;
     __syncthreads();
   }
   const uint32_t nop = ev_rank((uint32_t)s) | EV_M | EV_D;
-  for (uint32_t c = c0 + wid; c < c1; c += L2E_THREADS / 32) {
+  const uint32_t bmax = (uint32_t)(NB - 1);
+  // rank of h in Q: directory, then two probes (the sentinels and the sorted order make them unconditional)
+  auto rank_of = [&](uint32_t h, bool &match) -> uint32_t {
+    uint32_t j = tab[min(h >> a.shiftA, bmax)];
+    const uint2 qq = QP[j];
+    const uint32_t q0 = qq.x, q1 = qq.y;
+    match = (q0 == h) || (q1 == h);
+    j += (q0 < h) + (q1 < h);
+    if (q1 < h) { while (Q[j] < h) j++; match = Q[j] == h; }              // crowded bucket (rare)
+    return j;
+  };
+  for (uint32_t c = c0 + wid; c < c1; c += NW) {
     const uint32_t nEv = a.cNEv[c];
     if (nEv == 0) continue;
     const uint32_t b0 = a.cB0[c], nInit = a.cE0[c] - b0, nAll = a.cLast[c] - b0;
     const uint32_t sb = a.cOff[c];
+    const uint32_t mbk = a.cMB[c];
     uint16_t *ev = a.events;
+    if (mbk != 0xFFFFu) {
+      // ---- staged: compact records in, whole 32-byte steps out
+      const uint2 *rp = a.rec8 + b0;
+      const uint32_t nIt = (nAll + 31) >> 5, nSteps = (nEv + 15) >> 4;
+      uint32_t baseStep = 0;
+      uint2 nxt = make_uint2(0u, 0u);
+      if ((uint32_t)lane < nAll) nxt = __ldg(rp + lane);
+      for (uint32_t it = 0; it < nIt; it++) {
+        const uint32_t rb = it * 32 + lane;
+        const uint2 rc = nxt;
+        if (rb + 32 < nAll) nxt = __ldg(rp + rb + 32);
+        if (rb < nAll) {
+          bool match;
+          const uint32_t j = rank_of(rc.x, match);
+          const bool can = (int)j < s;                                        // rank s: above every query hash => no-op
+          const uint32_t code = ev_rank(j) | (match ? EV_M : 0u);
+          const uint32_t y = rc.y, back = y & 0x3FFFu, fwd = (y >> 14) & 0x3FFFu;
+          const uint32_t mb = min(back, rb);
+          // new distinct hash iff the previous twin is further than mb back: bit 29 says "further than back"; only a
+          // record of the FIRST window (mb = rb < back) with a nearer twin needs the exact distance
+          bool isNew = can && ((y >> 29) & 1u);
+          if (can && !((y >> 29) & 1u) && rb < back) isNew = (__ldg(&a.recLink[b0 + rb]) >> 16) > rb;
+          const bool sc = (rb + 1 >= nInit) && (rb + 1 != nAll);
+          ring[(rb * 2 - mb) & (L2E_RING - 1)] = (uint16_t)((isNew ? (code | EV_D) : nop) | (sc ? EV_S : 0u));
+          if (fwd != 0x3FFFu && rb + fwd < nAll) {
+            const bool gone = can && ((y >> 30) & 1u);
+            ring[(rb * 2 + fwd) & (L2E_RING - 1)] = (uint16_t)((gone ? code : nop) | (((y >> 28) & 1u) ? 0u : EV_S));
+          }
+        }
+        const bool lastIt = it + 1 == nIt;
+        if (lastIt || ((it + 1) % L2E_FLUSH_IT) == 0) {
+          if (lastIt && (uint32_t)lane < ((16u - (nEv & 15u)) & 15u)) ring[(nEv + lane) & (L2E_RING - 1)] = (uint16_t)nop;   // pad the last step
+          __syncwarp();
+          // every position below 64 * (it + 1) - max(back) belongs to a record already processed and is never written again
+          int fin = lastIt ? (int)nSteps : (((int)(64u * (it + 1)) - (int)mbk) >> 4);
+          if (fin > (int)nSteps) fin = (int)nSteps;
+          for (int k = (int)baseStep + lane; k < fin; k += 32) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(ring + ((k * 16) & (L2E_RING - 1)));
+            uint4 *dst = reinterpret_cast<uint4 *>(ev + ((size_t)sb + (size_t)k * 32) * 16);
+            const uint4 v0 = src[0], v1 = src[1];
+            dst[0] = v0; dst[1] = v1;
+          }
+          if (fin > (int)baseStep) baseStep = (uint32_t)fin;
+          __syncwarp();
+        }
+      }
+      continue;
+    }
+    // ---- direct: 16-byte records, 2-byte stores
     if (lane < ((16u - (nEv & 15u)) & 15u)) ev[ev_index(sb, nEv + lane)] = (uint16_t)nop;    // pad the last 32-byte step
     const uint4 *rp = a.rec + b0;
     uint32_t rb = lane;
@@ -463,14 +569,8 @@ l2_events_kernel(const L2PArgs a)
     for (; rb < nAll; rb += 32) {
       const uint4 rc = nxt;
       if (rb + 32 < nAll) nxt = __ldg(rp + rb + 32);
-      const uint32_t h = rc.x;
-      // rank of h in Q: directory, then two probes (the sentinels and the sorted order make them unconditional)
-      uint32_t j = tab[min(h >> a.shiftA, (uint32_t)(a.nBuckets - 1))];
-      const uint2 qq = QP[j];
-      const uint32_t q0 = qq.x, q1 = qq.y;
-      bool match = (q0 == h) || (q1 == h);
-      j += (q0 < h) + (q1 < h);
-      if (q1 < h) { while (Q[j] < h) j++; match = Q[j] == h; }              // crowded bucket (rare)
+      bool match;
+      const uint32_t j = rank_of(rc.x, match);
       const bool can = (int)j < s;                                          // rank s: above every query hash => no-op
       const uint32_t code = ev_rank(j) | (match ? EV_M : 0u);
       const uint32_t pd = rc.z >> 16, nd = rc.z & 0xFFFFu, back = rc.w & 0xFFFFu, fwd = rc.w >> 16;
@@ -807,18 +907,54 @@ __global__ void compact_sketch_kernel(const uint32_t *raw, const uint32_t *rawSt
 
 static constexpr uint64_t FRAG_MAX = 1u << 19;       // fragments per piece
 
+// A query as the sketch stage sees it: a contig-length table plus either the packed bases (stage A) or the first contig
+// ordinal inside the hint index (stage A': the genome is a member of the index, its bases are not needed).
+struct QuerySrc { const Genome *G; int32_t nContigs; const int32_t *len; int32_t member; };
+
+static QSketch *qsketch_build(Ctx *ctx, const std::vector<QuerySrc> &srcs, const int32_t *queryIds, const Index *hint);
+
 QSketch *qsketch_create(Ctx *ctx, const Genome *const *queries, int32_t nq, const int32_t *queryIds, const Index *hint)
 {
-  cudaStream_t st = ctx->stream;
-  const int k = ctx->prm.kmer_size, w = ctx->prm.window_size, fragLen = ctx->prm.frag_len;
-  if (fragLen < 1 || fragLen > 60000) fail(BANI_ERR_LIMIT, "fragment length %d outside the supported range [1, 60000]", fragLen);
+  const int k = ctx->prm.kmer_size, w = ctx->prm.window_size;
   const bool noReuse = !ctx->flags.sketchReuse;                                  // switch: always hash the queries
   if (hint && (noReuse || hint->device != ctx->device || hint->M == 0 || !hint->validBits.p || hint->k != k || hint->w != w)) hint = nullptr;
-  auto member = [&](const Genome *Q) -> int32_t {                                // first contig ordinal inside the hint index
-    if (!hint) return -1;
-    auto it = hint->members.find(Q->uid);
-    return it == hint->members.end() ? -1 : it->second;
-  };
+  std::vector<QuerySrc> srcs(nq);
+  for (int i = 0; i < nq; i++) {
+    const Genome *Q = queries[i];
+    if (!Q) fail(BANI_ERR_ARG, "null genome handle");
+    if (Q->device != ctx->device) fail(BANI_ERR_ARG, "genome lives on another device");
+    int32_t mem = -1;                                                            // first contig ordinal inside the hint index
+    if (hint) { auto it = hint->members.find(Q->uid); if (it != hint->members.end()) mem = it->second; }
+    srcs[i] = QuerySrc{Q, Q->nContigs, Q->len.data(), mem};
+  }
+  return qsketch_build(ctx, srcs, queryIds, hint);
+}
+
+// Fragment sketches of genomes of the index itself, by genome ordinal: needs nothing but the index (an index loaded
+// from disk serves as the query side of an all-vs-all run without any FASTA being read).
+QSketch *qsketch_from_index(Ctx *ctx, const Index *ix, const int32_t *ordinals, int32_t nq, const int32_t *queryIds)
+{
+  if (ix->device != ctx->device) fail(BANI_ERR_ARG, "index lives on another device");
+  if (ix->k != ctx->prm.kmer_size || ix->w != ctx->prm.window_size || ix->fragLen != ctx->prm.frag_len)
+    fail(BANI_ERR_ARG, "index was built with other parameters (k %d w %d fragLen %d)", ix->k, ix->w, ix->fragLen);
+  std::vector<QuerySrc> srcs(nq);
+  for (int i = 0; i < nq; i++) {
+    const int32_t g = ordinals[i];
+    if (g < 0 || g >= ix->nGenomes) fail(BANI_ERR_ARG, "genome ordinal %d outside the index (%d genomes)", g, ix->nGenomes);
+    const int32_t c0 = g ? ix->seqsByFile[g - 1] : 0, c1 = ix->seqsByFile[g];
+    srcs[i] = QuerySrc{nullptr, c1 - c0, ix->contigLen.data() + c0, c0};
+  }
+  if (ix->M == 0 || !ix->validBits.p) fail(BANI_ERR_ARG, "the index holds no minimizers: query sketches cannot be derived from it");
+  const Index *hint = ix;
+  return qsketch_build(ctx, srcs, queryIds, hint);
+}
+
+static QSketch *qsketch_build(Ctx *ctx, const std::vector<QuerySrc> &srcs, const int32_t *queryIds, const Index *hint)
+{
+  cudaStream_t st = ctx->stream;
+  const int32_t nq = (int32_t)srcs.size();
+  const int k = ctx->prm.kmer_size, w = ctx->prm.window_size, fragLen = ctx->prm.frag_len;
+  if (fragLen < 1 || fragLen > 60000) fail(BANI_ERR_LIMIT, "fragment length %d outside the supported range [1, 60000]", fragLen);
   auto qs = std::make_unique<QSketch>();
   qs->device = ctx->device; qs->k = k; qs->w = w; qs->fragLen = fragLen;
   qs->queryId.resize(nq); qs->totalFragments.assign(nq, 0);
@@ -833,26 +969,27 @@ QSketch *qsketch_create(Ctx *ctx, const Genome *const *queries, int32_t nq, cons
     bool pieceFromIndex = false;
     int q1 = q0;
     while (q1 < nq) {
-      const Genome *Q = queries[q1];
-      if (!Q) fail(BANI_ERR_ARG, "null genome handle");
-      if (Q->device != ctx->device) fail(BANI_ERR_ARG, "genome lives on another device");
+      const QuerySrc &qsrc = srcs[q1];
+      const Genome *Q = qsrc.G;
       uint64_t nf = 0;
-      for (int c = 0; c < Q->nContigs; c++) { int L = Q->len[c]; if (!(L < w || L < k || L < fragLen)) nf += L / fragLen; }
+      for (int c = 0; c < qsrc.nContigs; c++) { int L = qsrc.len[c]; if (!(L < w || L < k || L < fragLen)) nf += L / fragLen; }
       if (q1 > q0 && (uint64_t)F64 + nf > FRAG_MAX) break;
-      const int32_t mem = member(Q);
+      const int32_t mem = hint ? qsrc.member : -1;
+      if (mem < 0 && !Q) fail(BANI_ERR_INTERNAL, "query without bases and without an index to derive it from");
+      if (mem < 0) Q->wait_ready(st);                                  // its bases are hashed: the upload must have landed
       if (q1 > q0 && (mem >= 0) != pieceFromIndex) break;           // a piece is either derived from the index or hashed
       pieceFromIndex = mem >= 0;
       qFragOff.push_back((int32_t)F64);
       int32_t seqCounter = 0;
-      for (int c = 0; c < Q->nContigs; c++) {
-        const int L = Q->len[c];
+      for (int c = 0; c < qsrc.nContigs; c++) {
+        const int L = qsrc.len[c];
         if (L < w || L < k || L < fragLen) continue;                 // :138
         const int fc = L / fragLen;                                  // :152
         FragSrc sr;
-        sr.packed = Q->packed.p + Q->wordOff[c];
-        sr.nExc = (int32_t)(Q->excOff[c + 1] - Q->excOff[c]);
-        sr.excPos = sr.nExc ? Q->excPos.p + Q->excOff[c] : nullptr;
-        sr.excByte = sr.nExc ? Q->excByte.p + Q->excOff[c] : nullptr;
+        sr.packed = Q ? Q->packedBase() + Q->wordOff[c] : nullptr;
+        sr.nExc = Q ? (int32_t)(Q->excOff[c + 1] - Q->excOff[c]) : 0;
+        sr.excPos = sr.nExc ? Q->excPosBase() + Q->excOff[c] : nullptr;
+        sr.excByte = sr.nExc ? Q->excByteBase() + Q->excOff[c] : nullptr;
         sr.firstFrag = (int32_t)F64; sr.seqBase = seqCounter; sr.query = q1 - q0; sr.idxSeq = mem >= 0 ? mem + c : -1;
         src.push_back(sr);
         F64 += fc; seqCounter += fc;
@@ -1178,7 +1315,7 @@ void qsketch_map(Ctx *ctx, const Index *ix, const QSketch *const *sketches, int3
         BANI_SCRATCH(uint32_t, hitCnt, T + 1);
         BANI_SCRATCH(unsigned long long, hitOff, T + 1);
         { Stage sg(ctx, "lookup", 12.0 * T);
-          lookup_kernel<<<nblk(T + 1), 256, 0, st>>>(fragHash.p, segStart.p, sCount.p, F, (uint32_t)T, ix->ukeys.p, ix->uoff.p,
+          lookup_kernel<<<nblk(T + 1), 256, 0, st>>>(fragHash.p, (uint32_t)T, ix->tab.p, (1u << ix->tabBits) - 1u, ix->ukeys.p, ix->uoff.p,
                                                    ix->dir.p, ix->dirBits, hitLo.p, hitCnt.p);
           ctx->launches++;
           size_t tb = cub_scan_u64_temp(T + 1);
@@ -1217,7 +1354,7 @@ void qsketch_map(Ctx *ctx, const Index *ix, const QSketch *const *sketches, int3
             BANI_CUDA(cudaMemcpyAsync(hClass, classCount.p, sizeof hClass, cudaMemcpyDeviceToHost, st));
             BANI_CUDA(cudaStreamSynchronize(st));
             FragL1Args fa; fa.segStart = segStart.p; fa.sCount = sCount.p; fa.F = F; fa.hitLo = hitLo.p; fa.hitCnt = hitCnt.p; fa.hitOff = hitOff.p;
-            fa.posIdx = ix->posIdx.p; fa.recSeq = ix->seqId.p; fa.recWpos = ix->wpos.p; fa.minHits = ctx->d_minHits.p; fa.fragLen = fragLen;
+            fa.posIdx = ix->posIdx.p; fa.recPos = ix->pos8.p; fa.minHits = ctx->d_minHits.p; fa.fragLen = fragLen;
             fa.keyBits = 1; while (fa.keyBits < 32 && (1ull << fa.keyBits) < ix->M) fa.keyBits++;
             fa.stSeq = stSeq.p; fa.stStart = stStart.p; fa.stEnd = stEnd.p; fa.candCount = candCount.p;
             frag_l1_fast(ctx, fa, classList.p, hClass); }
@@ -1303,9 +1440,10 @@ void qsketch_map(Ctx *ctx, const Index *ix, const QSketch *const *sketches, int3
               L2PArgs lp; lp.cFrag = cFrag.p; lp.cSeq = cSeq.p; lp.cStart = cStart.p; lp.cEnd = cEnd.p; lp.C = C;
               lp.fragCandOff = fragCandOff.p; lp.fragHash = fragHash.p; lp.segStart = segStart.p; lp.sCount = sCount.p;
               lp.rec = ix->rec.p; lp.recWposSoA = ix->wpos.p; lp.contigRecOff = ix->contigRecOff.p; lp.fragLen = fragLen; lp.cmw = cmw;
+              lp.rec8 = ix->rec8.p; lp.recLink = ix->link.p; lp.blkMax = ix->blkMax.p;
               // fast path: needs the window links of the index (cmw >= 2) and ranks that fit the event code
               // (and whose per-warp state fits the shared-memory budget of l2_seq_kernel: larger sketches take l2_kernel)
-              lp.sLimit = (cmw >= 2 && ix->cmw == cmw) ? std::min(std::min(smax, L2_SMAX), L2_SHM_BUDGET / (L2S_WARPS * 32) - 2) : 0;
+              lp.sLimit = (cmw >= 2 && ix->cmw == cmw && ix->rec8.p) ? std::min(std::min(smax, L2_SMAX), L2_SHM_BUDGET / (L2S_WARPS * 32) - 2) : 0;
               // bucket width near 0 ~ 2^32 / (s * w): minimizer hashes are minima of w hashes, density w/2^32 at 0
               lp.nBuckets = ((uint64_t)C >= 8ull * (uint64_t)F) ? L2E_BUCKETS : 1024;      // few candidates per fragment: building a big directory is not worth it
               { const int forced = ctx->flags.l2eBuckets;
@@ -1318,6 +1456,8 @@ void qsketch_map(Ctx *ctx, const Index *ix, const QSketch *const *sketches, int3
               BANI_SCRATCH(uint32_t, cNEv, C);
               BANI_SCRATCH(uint32_t, cChunks, (size_t)C + 1);
               BANI_SCRATCH(uint32_t, cOff, (size_t)C + 1);
+              BANI_SCRATCH(uint16_t, cMB, (size_t)C + 1);
+              lp.cMB = cMB.p;
               lp.cB0 = cB0.p; lp.cE0 = cE0.p; lp.cLast = cLast.p; lp.cNEv = cNEv.p; lp.cChunks = cChunks.p; lp.cOff = cOff.p;
               lp.cPos = cPos.p; lp.cBest = cBest.p; lp.ctr_n2 = d_n2.p; lp.events = nullptr; lp.perm = nullptr;
               l2_bounds_kernel<<<nblk((uint64_t)C + 1), 256, 0, st>>>(lp); ctx->launches++;
@@ -1349,17 +1489,24 @@ void qsketch_map(Ctx *ctx, const Index *ix, const QSketch *const *sketches, int3
                 BANI_SCRATCH(uint16_t, events, (size_t)totalSteps * 16 + 64);
                 lp.events = events.p; lp.grpOff = grpOff.p;
                 l2_stream_base_kernel<<<nblk(C), 256, 0, st>>>(perm.p, grpOff.p, C, cOff.p); ctx->launches++;
-                const size_t shmE = 4 * ((size_t)lp.sLimit + 4) + 4 * (L2E_BUCKETS + 4) + 8 + 8 * ((size_t)lp.sLimit + 4);
+                // CTA size of the events kernel by candidates per fragment (warp per candidate: no idle warps in small shards)
+                const int evNT = ((uint64_t)C >= 6ull * (uint64_t)F) ? 256 : ((uint64_t)C >= 3ull * (uint64_t)F) ? 128 : 64;
+                const size_t shmE = 4 * ((size_t)(evNT / 32) * (L2E_RING / 2) + (size_t)lp.sLimit + 4 + L2E_BUCKETS + 4 + 2) + 8 * ((size_t)lp.sLimit + 4) + 16;
                 const size_t shmS = (size_t)L2S_WARPS * lp.warpBytes;
                 if (shmE > (size_t)L2_SHM_BUDGET || shmS > (size_t)L2_SHM_BUDGET) fail(BANI_ERR_INTERNAL, "L2 shared-memory budget exceeded");
                 if (ctx->first_time((const void *)l2_seq_kernel)) {
-                  BANI_CUDA(cudaFuncSetAttribute(l2_events_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L2_SHM_BUDGET));
+                  BANI_CUDA(cudaFuncSetAttribute(l2_events_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, L2_SHM_BUDGET));
+                  BANI_CUDA(cudaFuncSetAttribute(l2_events_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, L2_SHM_BUDGET));
+                  BANI_CUDA(cudaFuncSetAttribute(l2_events_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, L2_SHM_BUDGET));
                   BANI_CUDA(cudaFuncSetAttribute(l2_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L2_SHM_BUDGET));
                   BANI_CUDA(cudaFuncSetAttribute(l2_seq_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
                 }
                 sgb.stop();
                 { Stage sg(ctx, "l2_events"); idEv = sg.id(); evBytes = 32.0 * (double)totalSteps;
-                  l2_events_kernel<<<F, L2E_THREADS, shmE, st>>>(lp); ctx->launches++; }
+                  if (evNT == 256) l2_events_kernel<256><<<F, 256, shmE, st>>>(lp);
+                  else if (evNT == 128) l2_events_kernel<128><<<F, 128, shmE, st>>>(lp);
+                  else l2_events_kernel<64><<<F, 64, shmE, st>>>(lp);
+                  ctx->launches++; }
                 { Stage sg(ctx, "l2_seq", evBytes + 16.0 * C);       // the event codes in, {position, shared} out
                   l2_seq_kernel<<<nblk(C, L2S_WARPS * 32), L2S_WARPS * 32, shmS, st>>>(lp); ctx->launches++; }
               }

@@ -245,6 +245,116 @@ void genome_create_batch(Ctx *ctx, int32_t nGenomes, const int32_t *genOff, cons
   for (int g = 0; g < nGenomes; g++) out[g] = gs[g].release();
 }
 
+// ---- host-packed ingest ------------------------------------------------------
+// The same layout produced on the HOST by the reader threads (host_pack_contig below): 0.25 bytes per base cross PCIe
+// instead of 1, and nothing is left to do on the device but the copy.  The genomes of a batch are cut into upload
+// groups of <= 64 MB of packed words; each group is one GenomeBlock (one copy per array on the context's copy stream,
+// one event), so the index build can hash group g while group g+1 is still in flight.
+void genome_create_packed_batch(Ctx *ctx, int32_t nGenomes, const int32_t *genOff, const int32_t *contigLen, const int64_t *wordOff,
+                                const uint32_t *words, const int64_t *excOff, const uint32_t *excPos, const uint8_t *excByte,
+                                bool async, Genome **out)
+{
+  cudaStream_t cs = ctx->copyStream;
+  for (int g = 0; g < nGenomes; g++) out[g] = nullptr;
+  std::vector<std::unique_ptr<Genome>> gs(nGenomes);
+  const int32_t nC = nGenomes ? genOff[nGenomes] - genOff[0] : 0;
+  const int32_t cBase = nGenomes ? genOff[0] : 0;
+  // ---- validate the host tables before anything is allocated
+  for (int32_t c = 0; c < nC; c++) {
+    const int32_t L = contigLen[cBase + c];
+    const int64_t w0 = wordOff[cBase + c], need = ((int64_t)L + 15) / 16;
+    if (L < 0) fail(BANI_ERR_ARG, "negative contig length");
+    if (w0 < 0 || (w0 & 3)) fail(BANI_ERR_ARG, "packed contigs must start on a 16-byte boundary (word offset multiple of 4)");
+    if (c + 1 < nC && wordOff[cBase + c + 1] < w0 + need) fail(BANI_ERR_ARG, "packed contigs overlap or are out of order");
+    const int64_t e0 = excOff[cBase + c], e1 = excOff[cBase + c + 1];
+    if (e0 < 0 || e1 < e0) fail(BANI_ERR_ARG, "exception offsets must ascend");
+    for (int64_t e = e0; e < e1; e++) {
+      if (excPos[e] >= (uint32_t)L || (e > e0 && excPos[e] <= excPos[e - 1])) fail(BANI_ERR_ARG, "exception positions must ascend inside their contig");
+      const uint8_t b = excByte[e];
+      if (b == 'A' || b == 'C' || b == 'G' || b == 'T' || (b > 96 && b < 123)) fail(BANI_ERR_ARG, "an exception byte must be an upper-cased non-ACGT byte");
+    }
+  }
+  const int64_t GROUP_WORDS = std::max(1ll, ctx->flags.uploadGroupWords);
+  int g0 = 0;
+  while (g0 < nGenomes) {
+    // ---- one upload group = consecutive genomes
+    int g1 = g0; int64_t span = 0;
+    const int32_t ca = genOff[g0];
+    const int64_t wA = genOff[g0] < genOff[nGenomes] ? wordOff[ca] : 0;
+    while (g1 < nGenomes) {
+      const int32_t cLast = genOff[g1 + 1] - 1;
+      int64_t end = wA;
+      if (cLast >= genOff[g1]) end = wordOff[cLast] + (((int64_t)contigLen[cLast] + 15) / 16 + 3) / 4 * 4;
+      if (g1 > g0 && end - wA > GROUP_WORDS) break;
+      span = std::max(span, end - wA);
+      g1++;
+    }
+    const int32_t cb = genOff[g1];
+    const int64_t eA = excOff[ca], eB = excOff[cb];
+    auto blk = std::make_shared<GenomeBlock>();
+    blk->device = ctx->device;
+    blk->words.alloc((size_t)span + 8, cs);
+    if (span) BANI_CUDA(cudaMemcpyAsync(blk->words.p, words + wA, 4 * (size_t)span, cudaMemcpyHostToDevice, cs));
+    if (eB > eA) {
+      blk->excPos.alloc((size_t)(eB - eA), cs); blk->excByte.alloc((size_t)(eB - eA), cs);
+      BANI_CUDA(cudaMemcpyAsync(blk->excPos.p, excPos + eA, 4 * (size_t)(eB - eA), cudaMemcpyHostToDevice, cs));
+      BANI_CUDA(cudaMemcpyAsync(blk->excByte.p, excByte + eA, (size_t)(eB - eA), cudaMemcpyHostToDevice, cs));
+    }
+    BANI_CUDA(cudaEventCreateWithFlags(&blk->ready, cudaEventDisableTiming));
+    BANI_CUDA(cudaEventRecord(blk->ready, cs));
+    for (int g = g0; g < g1; g++) {
+      auto G = std::make_unique<Genome>();
+      G->device = ctx->device;
+      G->nContigs = genOff[g + 1] - genOff[g];
+      G->len.resize(G->nContigs); G->wordOff.resize(G->nContigs); G->excOff.assign(G->nContigs + 1, 0);
+      const int32_t c0 = genOff[g];
+      const int64_t wG = G->nContigs ? wordOff[c0] : wA, eG = excOff[c0];
+      for (int c = 0; c < G->nContigs; c++) {
+        G->len[c] = contigLen[c0 + c]; G->wordOff[c] = wordOff[c0 + c] - wG; G->excOff[c] = excOff[c0 + c] - eG; G->totalLen += (uint64_t)contigLen[c0 + c];
+      }
+      G->excOff[G->nContigs] = excOff[c0 + G->nContigs] - eG;
+      G->nExc = (uint64_t)G->excOff[G->nContigs];
+      G->blk = blk;
+      G->blkWords = blk->words.p + (wG - wA);
+      G->blkExcPos = blk->excPos.p ? blk->excPos.p + (eG - eA) : nullptr;
+      G->blkExcByte = blk->excByte.p ? blk->excByte.p + (eG - eA) : nullptr;
+      gs[g] = std::move(G);
+    }
+    g0 = g1;
+  }
+  if (!async) BANI_CUDA(cudaStreamSynchronize(cs));      // the host arrays may be released when the call returns
+  for (int g = 0; g < nGenomes; g++) out[g] = gs[g].release();
+}
+
+// 2-bit packing of one contig on the host: what pack_kernel / pack_exc_kernel do on the device (upper-case a-z, A C G T
+// -> 0 1 2 3, every other byte -> code 0 + an out-of-band (position, upper-cased byte) entry).  words: (len + 15) / 16
+// entries are written (the tail of the last word is code 0).  Returns the number of exceptions; only the first excCap are
+// stored, so a caller that sees a larger count retries with bigger arrays.
+uint64_t host_pack_contig(const uint8_t *seq, int64_t len, uint32_t *words, uint32_t *excPos, uint8_t *excByte, uint64_t excCap)
+{
+  static const struct Lut { uint8_t v[256]; Lut() { for (int i = 0; i < 256; i++) v[i] = 4; v['A'] = v['a'] = 0; v['C'] = v['c'] = 1; v['G'] = v['g'] = 2; v['T'] = v['t'] = 3; } } lut;
+  uint64_t nExc = 0;
+  const int64_t nw = (len + 15) / 16;
+  for (int64_t wi = 0; wi < nw; wi++) {
+    const int64_t p0 = wi * 16;
+    const int n = (int)std::min<int64_t>(16, len - p0);
+    uint32_t w = 0, any = 0;
+    for (int j = 0; j < n; j++) { const uint32_t c = lut.v[seq[p0 + j]]; w |= (c & 3u) << (2 * j); any |= c; }
+    if (any & 4u) {
+      for (int j = 0; j < n; j++) {
+        uint8_t b = seq[p0 + j];
+        if (lut.v[b] == 4) {
+          if (b > 96 && b < 123) b -= 32;                      // commonFunc.hpp:61-64 (only a-z; z and friends stay exceptions)
+          if (nExc < excCap) { excPos[nExc] = (uint32_t)(p0 + j); excByte[nExc] = b; }
+          nExc++;
+        }
+      }
+    }
+    words[wi] = w;
+  }
+  return nExc;
+}
+
 // ---- decode (test hook) ------------------------------------------------------
 __global__ void decode_kernel(const uint32_t *packed, const uint32_t *excPos, const uint8_t *excByte, int nExc,
                               int32_t len, uint8_t *out)
@@ -267,9 +377,10 @@ void genome_decode(Ctx *ctx, const Genome *g, int32_t contig, uint8_t *out, int6
   cudaStream_t st = ctx->stream;
   DevBuf<uint8_t> d(L, st);
   int nExc = (int)(g->excOff[contig + 1] - g->excOff[contig]);
-  decode_kernel<<<(L + 255) / 256, 256, 0, st>>>(g->packed.p + g->wordOff[contig], nullptr, nullptr, 0, L, d.p);
+  g->wait_ready(st);
+  decode_kernel<<<(L + 255) / 256, 256, 0, st>>>(g->packedBase() + g->wordOff[contig], nullptr, nullptr, 0, L, d.p);
   ctx->launches++;
-  if (nExc) decode_patch_kernel<<<(nExc + 255) / 256, 256, 0, st>>>(g->excPos.p + g->excOff[contig], g->excByte.p + g->excOff[contig], nExc, d.p);
+  if (nExc) decode_patch_kernel<<<(nExc + 255) / 256, 256, 0, st>>>(g->excPosBase() + g->excOff[contig], g->excByteBase() + g->excOff[contig], nExc, d.p);
   ctx->launches++;
   BANI_CUDA(cudaGetLastError());
   BANI_CUDA(cudaMemcpyAsync(out, d.p, L, cudaMemcpyDeviceToHost, st));

@@ -49,6 +49,7 @@ struct SketchArgs {
   unsigned long long *tileState;    // nTiles, zero-initialised
   unsigned long long *o_total;
   uint32_t *o_validBits; const unsigned long long *bitBase;   // optional: validity bitmap of the hashed positions
+  unsigned long long recBase;       // records written by earlier launches into the same arrays
 };
 
 // ------------------------------------------------------------------ MurmurHash3_x64_128, low 32 bits of h1
@@ -340,12 +341,12 @@ sketch_kernel(const SketchArgs a)
     if (lane == 0) {
       st[tile] = (2ull << 62) | (excl + total);
       s_base = excl;
-      if (t0 == 0 && a.o_segStart) a.o_segStart[seq] = (uint32_t)excl;
-      if (tile == a.nTiles - 1) { *a.o_total = excl + total; if (a.o_segStart) a.o_segStart[a.nSeq] = (uint32_t)(excl + total); }
+      if (t0 == 0 && a.o_segStart) a.o_segStart[seq] = (uint32_t)(a.recBase + excl);
+      if (tile == a.nTiles - 1) { *a.o_total = excl + total; if (a.o_segStart) a.o_segStart[a.nSeq] = (uint32_t)(a.recBase + excl + total); }
     }
   }
   __syncthreads();
-  unsigned long long o = s_base + wbase + (incl - cnt);
+  unsigned long long o = a.recBase + s_base + wbase + (incl - cnt);
 #pragma unroll 1
   for (uint32_t em = emit; em; em &= em - 1, o++) {
     const int j = __ffs(em) - 1;
@@ -370,14 +371,14 @@ static void launch_sketch(const SketchArgs &a, cudaStream_t st)
 
 uint64_t sketch_sequences(Ctx *ctx, const SeqDesc *d_desc, int32_t nSeq, const int32_t *h_len, int32_t uniformLen,
                           uint32_t *o_hash, int32_t *o_wpos, int32_t *o_seqId, uint64_t cap,
-                          uint32_t *o_segStart, uint32_t *o_validBits, const unsigned long long *bitBase)
+                          uint32_t *o_segStart, uint32_t *o_validBits, const unsigned long long *bitBase, uint64_t recBase)
 {
   cudaStream_t st = ctx->stream;
   const int k = ctx->prm.kmer_size, w = ctx->prm.window_size;
   if (k < 1 || k > SK_KMAX) fail(BANI_ERR_LIMIT, "k-mer size %d outside the supported range [1, %d]", k, SK_KMAX);
   if (w < 1 || w > SK_WMAX) fail(BANI_ERR_LIMIT, "window size %d outside the supported range [1, %d]", w, SK_WMAX);
   if (nSeq == 0) {
-    if (o_segStart) BANI_CUDA(cudaMemsetAsync(o_segStart, 0, 4, st));
+    if (o_segStart) { const uint32_t b = (uint32_t)recBase; BANI_CUDA(cudaMemcpyAsync(o_segStart, &b, 4, cudaMemcpyHostToDevice, st)); BANI_CUDA(cudaStreamSynchronize(st)); }
     return 0;
   }
   const int tileLen = (SK_SLOTS - 2 * (w - 1)) & ~31;        // multiple of 32: tiles write whole words of the validity bitmap
@@ -410,7 +411,7 @@ uint64_t sketch_sequences(Ctx *ctx, const SeqDesc *d_desc, int32_t nSeq, const i
   a.k = k; a.w = w; a.tileLen = tileLen;
   a.o_hash = o_hash; a.o_wpos = o_wpos; a.o_seqId = o_seqId; a.cap = cap; a.o_segStart = o_segStart;
   a.tileState = state.p; a.o_total = state.p + tiles;
-  a.o_validBits = o_validBits; a.bitBase = bitBase;
+  a.o_validBits = o_validBits; a.bitBase = bitBase; a.recBase = recBase;
   if (k == 16) launch_sketch<16>(a, st);
   else if (k == 21) launch_sketch<21>(a, st);
   else launch_sketch<0>(a, st);

@@ -46,6 +46,7 @@ struct Parameters {                                       // map_parameters.hpp:
   float maxRatioDiff = 100.0f;
   bool sanityCheck = false;
   int gpus = 0;                                           // extension: devices to shard the references over (0 = all visible)
+  std::string saveIndex, loadIndex;                       // extension: on-disk sketch cache (prefix of <prefix>.meta + <prefix>.<g>of<N>.idx)
   bani_params c() const
   {
     bani_params p; bani_params_default(&p);
@@ -69,30 +70,65 @@ struct DeviceGenome {
   ~DeviceGenome() { if (h) bani_genome_destroy(h); }
 };
 
-// Uploads genomes in batches through one pinned staging buffer (H2D + 2-bit packing on the device).
-inline void upload_genomes(bani_ctx *ctx, const std::vector<const bani_host::HostGenome *> &gs,
-                           std::vector<std::unique_ptr<DeviceGenome>> &out, size_t batchBytes = (size_t)1 << 30)
+// 2-bit packing on the host, in the reader thread that parsed the file (bani_pack_contig needs no GPU): the ASCII bytes
+// are released, a quarter of them (+ 5 bytes per non-ACGT byte) stay for the upload.
+inline void pack_genome(bani_host::HostGenome &g)
 {
-  void *stage = nullptr; size_t cap = 0;
+  if (g.packed) return;
+  int64_t words = 0;
+  g.wordOff.clear(); g.excOff.assign(1, 0);
+  for (const auto &c : g.contigs) { g.wordOff.push_back(words); words += (((int64_t)c.len + 15) / 16 + 3) / 4 * 4; }
+  g.words.assign((size_t)words + 8, 0u);
+  for (size_t i = 0; i < g.contigs.size(); i++) {
+    const auto &c = g.contigs[i];
+    if (c.len > 0x7fffffffull) throw std::runtime_error("contig " + c.name + " exceeds the int32 offset_t of the reference");
+    const size_t e0 = g.excPos.size();
+    uint64_t cap = std::max<uint64_t>(c.len / 64, 256), n = 0;
+    for (;;) {
+      g.excPos.resize(e0 + cap); g.excByte.resize(e0 + cap);
+      check(bani_pack_contig(g.seq.data() + c.off, (int64_t)c.len, g.words.data() + g.wordOff[i], g.excPos.data() + e0, g.excByte.data() + e0, cap, &n), "bani_pack_contig");
+      if (n <= cap) break;
+      cap = n;
+    }
+    g.excPos.resize(e0 + n); g.excByte.resize(e0 + n);
+    g.excOff.push_back((int64_t)(e0 + n));
+  }
+  std::vector<uint8_t>().swap(g.seq);
+  g.packed = true;
+}
+
+// Uploads host-packed genomes (bani_genome_create_packed_batch): the genomes of a batch are laid out back to back in one
+// host array per kind; the library copies them in groups on its copy stream.
+inline void upload_genomes(bani_ctx *ctx, const std::vector<const bani_host::HostGenome *> &gs,
+                           std::vector<std::unique_ptr<DeviceGenome>> &out, size_t batchWords = (size_t)1 << 28)
+{
   size_t i = 0;
   while (i < gs.size()) {
-    size_t j = i, bytes = 0;
-    while (j < gs.size() && (j == i || bytes + gs[j]->seq.size() <= batchBytes)) { bytes += gs[j]->seq.size(); j++; }
-    if (bytes > cap) { if (stage) bani_host_free(stage); cap = std::max(bytes, (size_t)1 << 20); check(bani_host_alloc(cap, &stage), "bani_host_alloc"); }
-    std::vector<int32_t> genOff(1, 0); std::vector<int64_t> off(1, 0);
-    size_t pos = 0;
-    for (size_t g = i; g < j; g++) {
-      memcpy((uint8_t *)stage + pos, gs[g]->seq.data(), gs[g]->seq.size());
-      for (const auto &c : gs[g]->contigs) off.push_back((int64_t)(pos + c.off + c.len));
-      pos += gs[g]->seq.size();
-      genOff.push_back((int32_t)(off.size() - 1));
+    size_t j = i, words = 0, exc = 0;
+    while (j < gs.size() && (j == i || words + gs[j]->words.size() <= batchWords)) {
+      if (!gs[j]->packed) throw std::runtime_error("upload_genomes: genome " + gs[j]->path + " has not been packed");
+      words += gs[j]->words.size(); exc += gs[j]->excPos.size(); j++;
     }
+    std::vector<uint32_t> w(words + 8, 0u), ep(exc + 1); std::vector<uint8_t> eb(exc + 1);
+    std::vector<int32_t> genOff(1, 0), clen; std::vector<int64_t> woff, eoff(1, 0);
+    size_t wp = 0, epos = 0;
+    for (size_t g = i; g < j; g++) {
+      const auto &G = *gs[g];
+      memcpy(w.data() + wp, G.words.data(), 4 * G.words.size());
+      if (!G.excPos.empty()) { memcpy(ep.data() + epos, G.excPos.data(), 4 * G.excPos.size()); memcpy(eb.data() + epos, G.excByte.data(), G.excByte.size()); }
+      for (size_t c = 0; c < G.contigs.size(); c++) {
+        clen.push_back((int32_t)G.contigs[c].len); woff.push_back((int64_t)wp + G.wordOff[c]); eoff.push_back((int64_t)epos + G.excOff[c + 1]);
+      }
+      wp += G.words.size(); epos += G.excPos.size();
+      genOff.push_back((int32_t)clen.size());
+    }
+    clen.push_back(0); woff.push_back((int64_t)wp);
     std::vector<bani_genome *> hs(j - i, nullptr);
-    check(bani_genome_create_batch(ctx, (int32_t)(j - i), genOff.data(), off.data(), (const uint8_t *)stage, hs.data()), "bani_genome_create_batch");
+    check(bani_genome_create_packed_batch(ctx, (int32_t)(j - i), genOff.data(), clen.data(), woff.data(), w.data(), eoff.data(), ep.data(), eb.data(),
+                                          /*async=*/0, hs.data()), "bani_genome_create_packed_batch");
     for (size_t g = i; g < j; g++) { auto d = std::make_unique<DeviceGenome>(); d->h = hs[g - i]; d->host = gs[g]; out.push_back(std::move(d)); }
     i = j;
   }
-  if (stage) bani_host_free(stage);
 }
 
 // ---------------------------------------------------------------------------------------- Sketch (HP1)
@@ -110,6 +146,19 @@ class Sketch {
     }
     check(bani_index_build(ctx, hs.data(), (int32_t)hs.size(), &ix_), "bani_index_build");
   }
+  // From the on-disk sketch cache (bani_index_load): lengths and the genome table come from the file, contig names from
+  // the caller's metadata (one per contig; may be empty when no --visualize output is wanted)
+  Sketch(bani_ctx *ctx, const Parameters &p, const std::string &indexFile, const std::vector<std::string> &contigNames) : ctx_(ctx), param_(p)
+  {
+    check(bani_index_load(ctx, indexFile.c_str(), &ix_), "bani_index_load");
+    uint64_t nMin = 0, nUniq = 0, totalLen = 0, nc = 0, ng = 0;
+    check(bani_index_stats(ix_, &nMin, &nUniq, &totalLen, &nc, &ng), "bani_index_stats");
+    std::vector<int32_t> cl(std::max<uint64_t>(nc, 1)), sbf(std::max<uint64_t>(ng, 1));
+    check(bani_index_contigs(ix_, cl.data(), cl.size(), sbf.data(), sbf.size()), "bani_index_contigs");
+    for (uint64_t c = 0; c < nc; c++) metadata.push_back(ContigInfo{c < contigNames.size() ? contigNames[c] : std::string(), (offset_t)cl[c]});
+    for (uint64_t g = 0; g < ng; g++) sequencesByFileInfo.push_back((int)sbf[g]);
+  }
+  void save(const std::string &indexFile) const { check(bani_index_save(ctx_, ix_, indexFile.c_str()), "bani_index_save"); }
   ~Sketch() { if (ix_) bani_index_destroy(ix_); }
   Sketch(const Sketch &) = delete; Sketch &operator=(const Sketch &) = delete;
   const bani_index *handle() const { return ix_; }
@@ -178,6 +227,14 @@ inline uint64_t genomeLength(const bani_host::HostGenome &g, int fragLen)
 {
   uint64_t s = 0;
   for (const auto &c : g.contigs) if ((int64_t)c.len >= fragLen) s += (c.len / (uint64_t)fragLen) * (uint64_t)fragLen;
+  return s;
+}
+
+// the same from a contig-length table (a reference genome known only through a loaded index)
+inline uint64_t genomeLength(const std::vector<skch::ContigInfo> &meta, int c0, int c1, int fragLen)
+{
+  uint64_t s = 0;
+  for (int c = c0; c < c1; c++) if ((int64_t)meta[c].len >= fragLen) s += ((uint64_t)meta[c].len / (uint64_t)fragLen) * (uint64_t)fragLen;
   return s;
 }
 

@@ -8,6 +8,8 @@
 //     -t sets the host threads of the ingest stage.  Results do not depend on the split.
 //   * every genome file is read ONCE (parallel inflate + parse), its length for the --minFraction filter comes from
 //     the same pass (the reference reads each file again in computeGenomeLengths, computeCoreIdentity.hpp:48-92)
+//   * --saveIndex / --loadIndex: the on-disk sketch cache the reference lacks (its only answer to repeated runs is
+//     scripts/splitDatabase.sh + README.md:104-106); parameters (k, fragLen, window) are stored and a mismatch is refused
 //   * without --visualize the per-pair reduction runs on the device (bani_map_cgi); with it, the mapping rows come
 //     back and cgi::computeCGI runs on the host because the .visual file needs the surviving rows themselves
 #include <atomic>
@@ -43,6 +45,9 @@ static void usage(const char *prog, std::ostream &o)
        "     --minFraction <value> minimum fraction of genome that must be shared for trusting ANI [default : 0.2]\n"
        "     --maxRatioDiff <value> maximum difference between (Total Ref. Length/Total Occ. Hashes) and\n"
        "                           (Total Ref. Length/Total No. Hashes) [default : 100.0]\n"
+       "     --saveIndex <prefix>  write the reference sketches to <prefix>.meta + <prefix>.<shard>of<N>.idx after building them\n"
+       "     --loadIndex <prefix>  take the references from a saved index instead of -r/--rl: no reference file is read or\n"
+       "                           sketched again; queries that are genomes of the index need no file either (1 GPU)\n"
        "     --visualize           output mappings for visualization (<output>.visual)\n"
        "     --matrix              also output ANI values as lower triangular matrix (<output>.matrix)\n"
        "     -o, --output <value>  output file name\n"
@@ -91,6 +96,8 @@ static void parseandSave(int argc, char **argv, Parameters &p)
     else if (a == "--fragLen") p.minReadLength = atoi(need(i));
     else if (a == "--minFraction") p.minFraction = (float)atof(need(i));
     else if (a == "--maxRatioDiff") p.maxRatioDiff = (float)atof(need(i));
+    else if (a == "--saveIndex") p.saveIndex = need(i);
+    else if (a == "--loadIndex") p.loadIndex = need(i);
     else if (a == "--visualize") p.visualize = true;
     else if (a == "--matrix") p.matrixOutput = true;
     else if (a == "-o" || a == "--output") p.outFileName = need(i);
@@ -100,9 +107,11 @@ static void parseandSave(int argc, char **argv, Parameters &p)
   }
   if (help) { usage(argv[0], std::cout); exit(0); }
   if (version) { std::cerr << "version 1.33 (" << bani_version() << ")\n\n"; exit(0); }
-  if (refName.empty() && refList.empty()) { std::cerr << "Provide reference file (s)\n"; exit(1); }
+  if (!p.loadIndex.empty() && (!refName.empty() || !refList.empty())) { std::cerr << "ERROR, --loadIndex replaces -r/--rl: give one of them\n"; exit(1); }
+  if (!p.loadIndex.empty() && !p.saveIndex.empty()) { std::cerr << "ERROR, --saveIndex and --loadIndex exclude each other\n"; exit(1); }
+  if (refName.empty() && refList.empty() && p.loadIndex.empty()) { std::cerr << "Provide reference file (s)\n"; exit(1); }
   if (qryName.empty() && qryList.empty()) { std::cerr << "Provide query file (s)\n"; exit(1); }
-  if (!refName.empty()) p.refSequences.push_back(refName); else parseFileList(refList, p.refSequences);
+  if (!refName.empty()) p.refSequences.push_back(refName); else if (!refList.empty()) parseFileList(refList, p.refSequences);
   if (!qryName.empty()) p.querySequences.push_back(qryName); else parseFileList(qryList, p.querySequences);
   if (!(p.minFraction >= 0.0f && p.minFraction <= 1.0f)) { std::cerr << "ERROR, --minFraction must lie in [0, 1]\n"; exit(1); }
   if (p.threads < 1) p.threads = 1;
@@ -116,7 +125,43 @@ static void parseandSave(int argc, char **argv, Parameters &p)
   for (size_t i = 0; i < p.querySequences.size(); i++) std::cerr << (i ? ", " : "") << p.querySequences[i];
   std::cerr << "]\nKmer size = " << p.kmerSize << "\nFragment length = " << p.minReadLength << "\nThreads = " << p.threads
             << "\nANI output file = " << p.outFileName << "\nSanity Check  = " << p.sanityCheck << "\n>>>>>>>>>>>>>>>>>>" << std::endl;
-  validateInputFiles(p.querySequences, p.refSequences);
+  if (p.loadIndex.empty()) validateInputFiles(p.querySequences, p.refSequences);
+}
+
+// ---- metadata of a saved index: what the flat per-shard files (bani_index_save) do not hold -- genome paths and
+//      contig names -- plus the parameters, so that a mismatch is reported before any GPU work
+struct IndexMeta {
+  int k = 0, fragLen = 0, window = 0, shards = 0;
+  std::vector<std::string> refPaths;                                  // global reference order
+  std::vector<std::vector<std::string>> contigNames;                  // per shard, seqId order
+};
+static std::string shardFile(const std::string &prefix, int g, int G) { return prefix + "." + std::to_string(g) + "of" + std::to_string(G) + ".idx"; }
+
+static void writeMeta(const std::string &prefix, const Parameters &p, int G, const std::vector<std::vector<std::string>> &contigNames)
+{
+  std::ofstream o(prefix + ".meta");
+  if (!o) throw std::runtime_error("cannot write " + prefix + ".meta");
+  o << "BANI_INDEX_META\t1\n" << p.kmerSize << "\t" << p.minReadLength << "\t" << p.windowSize << "\t" << G << "\t" << p.refSequences.size() << "\n";
+  for (const auto &r : p.refSequences) o << r << "\n";
+  for (int g = 0; g < G; g++) { o << contigNames[g].size() << "\n"; for (const auto &n : contigNames[g]) o << n << "\n"; }
+}
+
+static IndexMeta readMeta(const std::string &prefix)
+{
+  std::ifstream in(prefix + ".meta");
+  if (!in) throw std::runtime_error("cannot open " + prefix + ".meta");
+  IndexMeta m; std::string tag; int ver = 0; size_t nRefs = 0;
+  in >> tag >> ver >> m.k >> m.fragLen >> m.window >> m.shards >> nRefs;
+  if (!in || tag != "BANI_INDEX_META" || ver != 1 || m.shards < 1) throw std::runtime_error(prefix + ".meta is not an index metadata file");
+  std::string line; std::getline(in, line);
+  for (size_t i = 0; i < nRefs; i++) { if (!std::getline(in, line)) throw std::runtime_error(prefix + ".meta is truncated"); m.refPaths.push_back(line); }
+  m.contigNames.resize(m.shards);
+  for (int g = 0; g < m.shards; g++) {
+    if (!std::getline(in, line)) throw std::runtime_error(prefix + ".meta is truncated");
+    const size_t n = (size_t)std::stoull(line);
+    for (size_t i = 0; i < n; i++) { if (!std::getline(in, line)) throw std::runtime_error(prefix + ".meta is truncated"); m.contigNames[g].push_back(line); }
+  }
+  return m;
 }
 
 int main(int argc, char **argv)
@@ -146,17 +191,37 @@ int main(int argc, char **argv)
   parseandSave(argc, argv, parameters);
   const std::string fileName = parameters.outFileName;
   try {
-    // ---- ingest: every distinct file once, in parallel
+    const bool loading = !parameters.loadIndex.empty();
+    IndexMeta meta;
+    if (loading) {
+      meta = readMeta(parameters.loadIndex);
+      if (meta.k != parameters.kmerSize || meta.fragLen != parameters.minReadLength || meta.window != parameters.windowSize)
+        throw std::runtime_error("the saved index was built with k " + std::to_string(meta.k) + " fragLen " + std::to_string(meta.fragLen) + " window " + std::to_string(meta.window) +
+                                 ", this run asks for k " + std::to_string(parameters.kmerSize) + " fragLen " + std::to_string(parameters.minReadLength) + " window " + std::to_string(parameters.windowSize));
+      parameters.refSequences = meta.refPaths;
+    }
+    int32_t nDev = 0;
+    if (bani_device_count(&nDev) != BANI_OK || nDev == 0) throw std::runtime_error("no CUDA device available (this program has no CPU path)");
+    const int G = loading ? meta.shards : (parameters.gpus > 0 ? std::min(parameters.gpus, nDev) : nDev);
+    if (G > nDev) throw std::runtime_error("the saved index has " + std::to_string(G) + " shards but only " + std::to_string(nDev) + " GPU(s) are visible");
+    const auto shards = cgi::splitReferenceGenomes((int)parameters.refSequences.size(), G);
+
+    // ---- ingest: every distinct file once, in parallel.  With a loaded index no reference file is read, and (one
+    //      shard, no --visualize) neither is a query that is a genome of the index: its sketch is derived from the index
     auto t0 = Clock::now();
+    std::unordered_map<std::string, int> refOrdinal;                  // path -> first position in the reference list
+    for (size_t j = 0; j < parameters.refSequences.size(); j++) refOrdinal.emplace(parameters.refSequences[j], (int)j);
+    const bool deriveQueries = loading && G == 1 && !parameters.visualize;
+    auto derivable = [&](const std::string &q) { return deriveQueries && refOrdinal.count(q) > 0; };
     std::unordered_map<std::string, int> pathId; std::vector<std::string> paths;
-    for (const auto *lst : {&parameters.querySequences, &parameters.refSequences})
-      for (const auto &e : *lst) if (!pathId.count(e)) { pathId[e] = (int)paths.size(); paths.push_back(e); }
+    for (const auto &e : parameters.querySequences) if (!derivable(e) && !pathId.count(e)) { pathId[e] = (int)paths.size(); paths.push_back(e); }
+    if (!loading) for (const auto &e : parameters.refSequences) if (!pathId.count(e)) { pathId[e] = (int)paths.size(); paths.push_back(e); }
     std::vector<bani_host::HostGenome> genomes(paths.size());
     {
       std::atomic<size_t> next(0); std::mutex emu; std::string err;
       auto work = [&]() {
         for (size_t i; (i = next++) < paths.size();) {
-          try { genomes[i] = bani_host::read_genome(paths[i]); }
+          try { genomes[i] = bani_host::read_genome(paths[i]); skch::pack_genome(genomes[i]); }     // parse + 2-bit pack in the reader thread
           catch (const std::exception &e) { std::lock_guard<std::mutex> l(emu); err = e.what(); }
         }
       };
@@ -170,14 +235,10 @@ int main(int argc, char **argv)
     std::cerr << "INFO, skch::main, Time spent reading " << paths.size() << " genome files : "
               << std::chrono::duration<double>(Clock::now() - t0).count() << " sec" << std::endl;
 
-    // ---- one reference shard per GPU
-    int32_t nDev = 0;
-    if (bani_device_count(&nDev) != BANI_OK || nDev == 0) throw std::runtime_error("no CUDA device available (this program has no CPU path)");
-    const int G = parameters.gpus > 0 ? std::min(parameters.gpus, nDev) : nDev;
-    const auto shards = cgi::splitReferenceGenomes((int)parameters.refSequences.size(), G);
     std::vector<cgi::CGI_Results> finalResults;
     std::vector<std::string> visual(G);
     std::vector<char> sanity(G, 1); std::vector<float> ratioDiffs(G, 1.0f);
+    std::vector<std::vector<std::string>> savedContigNames(G);
     std::mutex mu; std::string err;
 
     auto shardWork = [&](int g) {
@@ -187,21 +248,39 @@ int main(int argc, char **argv)
         bani_ctx *ctx = nullptr;
         check(bani_ctx_create(g, &cp, &ctx), "bani_ctx_create");
         {
-          // genomes this device needs: its reference shard and every query, each file once
+          // genomes this device needs: its reference shard (unless loaded) and every query that has to be read, each file once
           std::vector<int> need; std::unordered_map<int, int> slot;
           auto want = [&](const std::string &path) { const int id = pathId.at(path); if (!slot.count(id)) { slot[id] = (int)need.size(); need.push_back(id); } return slot[id]; };
-          std::vector<int> refSlot, qrySlot;
-          for (int j : shards[g]) refSlot.push_back(want(parameters.refSequences[j]));
-          for (const auto &q : parameters.querySequences) qrySlot.push_back(want(q));
+          std::vector<int> refSlot, qrySlot;                              // qrySlot: -1 = derived from the index
+          if (!loading) for (int j : shards[g]) refSlot.push_back(want(parameters.refSequences[j]));
+          for (const auto &q : parameters.querySequences) qrySlot.push_back(derivable(q) ? -1 : want(q));
           std::vector<const bani_host::HostGenome *> hs; for (int id : need) hs.push_back(&genomes[id]);
           std::vector<std::unique_ptr<DeviceGenome>> dev;
           upload_genomes(ctx, hs, dev);
-          std::vector<const DeviceGenome *> refs; std::vector<std::string> shardRefNames;
-          for (size_t i = 0; i < refSlot.size(); i++) { refs.push_back(dev[refSlot[i]].get()); shardRefNames.push_back(parameters.refSequences[shards[g][i]]); }
+          std::vector<std::string> shardRefNames;
+          for (int j : shards[g]) shardRefNames.push_back(parameters.refSequences[j]);
 
-          Sketch referSketch(ctx, parameters, refs);                      // HP1
-          if (g == 0) std::cerr << "INFO [GPU 0], skch::main, Time spent sketching the reference : "
+          std::unique_ptr<Sketch> referSketchP;                           // HP1, or the cache
+          if (loading) referSketchP.reset(new Sketch(ctx, parameters, shardFile(parameters.loadIndex, g, G), meta.contigNames[g]));
+          else {
+            std::vector<const DeviceGenome *> refs;
+            for (int sl : refSlot) refs.push_back(dev[sl].get());
+            referSketchP.reset(new Sketch(ctx, parameters, refs));
+          }
+          Sketch &referSketch = *referSketchP;
+          if (g == 0) std::cerr << "INFO [GPU 0], skch::main, Time spent " << (loading ? "loading" : "sketching") << " the reference : "
                                 << std::chrono::duration<double>(Clock::now() - t1).count() << " sec" << std::endl;
+          if (!parameters.saveIndex.empty()) {
+            referSketch.save(shardFile(parameters.saveIndex, g, G));
+            for (const auto &c : referSketch.metadata) savedContigNames[g].push_back(c.name);
+          }
+          if (loading) {                                                  // lengths of the shard's genomes for the --minFraction filter
+            std::lock_guard<std::mutex> l(mu);
+            for (size_t i = 0; i < shards[g].size(); i++) {
+              const int c0 = i ? referSketch.sequencesByFileInfo[i - 1] : 0, c1 = referSketch.sequencesByFileInfo[i];
+              genomeLengths.emplace(shardRefNames[i], cgi::genomeLength(referSketch.metadata, c0, c1, parameters.minReadLength));
+            }
+          }
           std::vector<cgi::CGI_Results> local;
           sanity[g] = referSketch.sanityCheck(parameters.maxRatioDiff); ratioDiffs[g] = referSketch.getRatioDifference();
           if (sanity[g]) {
@@ -217,9 +296,19 @@ int main(int argc, char **argv)
               }
               visual[g] = vis.str();
             } else {
-              std::vector<bani_genome *> qh; for (int s : qrySlot) qh.push_back(dev[s]->h);
-              bani_cgi_result *res = nullptr; uint64_t n = 0; std::vector<uint64_t> tot(qh.size()); bani_map_counters ctr;
-              check(bani_map_cgi(ctx, referSketch.handle(), qh.data(), (int32_t)qh.size(), &res, &n, tot.data(), &ctr), "bani_map_cgi");   // HP2 + reduction
+              // HP2 + reduction for all queries: one sketch object for the queries that were read, one for those derived
+              std::vector<bani_genome *> qh; std::vector<int32_t> qid, dord, did;
+              for (size_t q = 0; q < qrySlot.size(); q++) {
+                if (qrySlot[q] >= 0) { qh.push_back(dev[qrySlot[q]]->h); qid.push_back((int32_t)q); }
+                else { dord.push_back(refOrdinal.at(parameters.querySequences[q])); did.push_back((int32_t)q); }
+              }
+              std::vector<bani_qsketch *> sk;
+              if (!qh.empty()) { bani_qsketch *s = nullptr; check(bani_qsketch_create(ctx, qh.data(), (int32_t)qh.size(), qid.data(), referSketch.handle(), &s), "bani_qsketch_create"); sk.push_back(s); }
+              if (!dord.empty()) { bani_qsketch *s = nullptr; check(bani_qsketch_from_index(ctx, referSketch.handle(), dord.data(), (int32_t)dord.size(), did.data(), &s), "bani_qsketch_from_index"); sk.push_back(s); }
+              bani_cgi_result *res = nullptr; uint64_t n = 0; bani_map_counters ctr;
+              const int rc = bani_map_cgi_sketch(ctx, referSketch.handle(), sk.data(), (int32_t)sk.size(), &res, &n, &ctr);     // HP2 + reduction
+              for (auto *s : sk) bani_qsketch_destroy(s);
+              check(rc, "bani_map_cgi_sketch");
               for (uint64_t i = 0; i < n; i++)
                 local.push_back(cgi::CGI_Results{res[i].refGenomeId, res[i].qryGenomeId, res[i].countSeq, res[i].totalQueryFragments, res[i].identity});
               bani_free(res);
@@ -240,8 +329,11 @@ int main(int argc, char **argv)
       for (auto &t : th) t.join();
     }
     if (!err.empty()) throw std::runtime_error(err);
+    if (!parameters.saveIndex.empty()) writeMeta(parameters.saveIndex, parameters, G, savedContigNames);
     for (int g = 0; g < G; g++)
       if (!sanity[g]) std::cerr << "ERROR :: SPLIT " << g << "'s ratio difference " << ratioDiffs[g] << " exceeds maximum thresholds." << std::endl;
+    // a query derived from the index has the length its reference twin has
+    for (const auto &q : parameters.querySequences) if (!genomeLengths.count(q)) throw std::runtime_error("no length known for " + q);
 
     cgi::outputCGI(parameters, genomeLengths, finalResults, fileName);
     if (parameters.matrixOutput) cgi::outputPhylip(parameters, genomeLengths, finalResults, fileName);

@@ -24,7 +24,13 @@ struct Contig { std::string name; uint64_t off = 0; uint64_t len = 0; };   // by
 struct HostGenome {
   std::string path;
   std::vector<Contig> contigs;
-  std::vector<uint8_t> seq;          // all contigs back to back, bytes exactly as kseq yields them
+  std::vector<uint8_t> seq;          // all contigs back to back, bytes exactly as kseq yields them (released once packed)
+  // 2-bit packed form (filled by skch::pack_genome in the reader thread): what crosses PCIe
+  std::vector<uint32_t> words;       // every contig starts on a multiple of 4 words
+  std::vector<int64_t> wordOff;      // per contig
+  std::vector<uint32_t> excPos; std::vector<uint8_t> excByte;
+  std::vector<int64_t> excOff;       // per contig + 1
+  bool packed = false;
 };
 
 inline std::vector<uint8_t> inflate_file(const std::string &path)

@@ -116,7 +116,7 @@ BANI_API void *bani_ctx_stream(bani_ctx *ctx);
 
 /* Run-time switches of a context.  name: "sketch_reuse" (1 = read the fragment sketches of index members from the
  * index, 0 = always hash the query fragments: what a run with --ql != --rl does), "max_hits_per_piece",
- * "frag_l1_max", "l2e_buckets" (tuning / test switches of the mapping pipeline; results never depend on them). */
+ * "frag_l1_max", "l2e_buckets", "upload_group_words" (tuning / test switches; results never depend on them). */
 BANI_API int  bani_ctx_set_flag(bani_ctx *ctx, const char *name, int64_t value);
 
 /* Per-stage device timing.  When enabled, every stage of HP1/HP2 is bracketed by CUDA events on
@@ -148,6 +148,22 @@ BANI_API int  bani_genome_create(bani_ctx *ctx, int32_t n_contigs, const int64_t
  * genome g owns contigs [gen_off[g], gen_off[g+1]) of the off[] table. */
 BANI_API int  bani_genome_create_batch(bani_ctx *ctx, int32_t n_genomes, const int32_t *gen_off,
                                        const int64_t *off, const uint8_t *seq, bani_genome **out);
+/* Host-packed ingest: the 2-bit layout of the device (16 bases per uint32, A0 C1 G2 T3, base i in bits [2*(i%16), +2);
+ * every other byte after upper-casing a-z is code 0 plus an out-of-band (contig-relative position, byte) entry) produced
+ * on the HOST -- by the reader threads, as the bytes come off kseq_read -- so that 0.25 bytes per base cross PCIe instead
+ * of 1.  bani_pack_contig needs no GPU; it writes (len + 15) / 16 words and returns the exception count through *n_exc
+ * (only the first exc_cap are stored: retry with larger arrays if it is bigger).
+ * bani_genome_create_packed_batch: contig c of the batch has contig_len[c] bases at words + word_off[c] (multiple of 4,
+ * ascending, no overlap) and its exceptions at [exc_off[c], exc_off[c+1]); genome g owns contigs
+ * [gen_off[g], gen_off[g+1]).  The copies run on a second stream in groups of <= 64 MB so that an index build that
+ * follows hashes the first groups while the last are in flight.  async = 0: the call returns when the copies are done;
+ * async != 0: it returns at once and the host arrays (pinned) must stay untouched until the genomes have been consumed
+ * by a call that returns results (bani_index_build, bani_map_*, bani_qsketch_create) or bani_ctx_sync. */
+BANI_API int  bani_pack_contig(const uint8_t *seq, int64_t len, uint32_t *words, uint32_t *exc_pos, uint8_t *exc_byte,
+                               uint64_t exc_cap, uint64_t *n_exc);
+BANI_API int  bani_genome_create_packed_batch(bani_ctx *ctx, int32_t n_genomes, const int32_t *gen_off, const int32_t *contig_len,
+                                              const int64_t *word_off, const uint32_t *words, const int64_t *exc_off,
+                                              const uint32_t *exc_pos, const uint8_t *exc_byte, int32_t async, bani_genome **out);
 BANI_API void bani_genome_destroy(bani_genome *g);
 BANI_API int  bani_genome_info(const bani_genome *g, int32_t *n_contigs, uint64_t *total_len,
                                uint64_t *n_exceptions, uint64_t *n_fragments);
@@ -169,6 +185,18 @@ BANI_API int  bani_index_minimizers(bani_ctx *ctx, const bani_index *ix, bani_mi
  * Returns the count through *n; writes at most cap (seqId, wpos) pairs. */
 BANI_API int  bani_index_lookup(bani_ctx *ctx, const bani_index *ix, uint32_t hash,
                                 int32_t *seqId, int32_t *wpos, uint64_t cap, uint64_t *n);
+
+/* ---- on-disk sketch cache (the reference has none: scripts/splitDatabase.sh + README.md:104-106 re-sketch every
+ * reference in every run).  bani_index_save writes what only the sketch launch can produce -- position-ordered
+ * (hash, wpos) records, contig table, validity bitmap, parameters, checksum -- as one flat file; bani_index_load reads
+ * it back on a context with the SAME k / window / fragLen (anything else is refused, like an in-memory mismatch) and
+ * rebuilds the lookup side on the GPU.  Host metadata (genome paths, contig names) is the caller's to store. */
+BANI_API int  bani_index_save(bani_ctx *ctx, const bani_index *ix, const char *path);
+BANI_API int  bani_index_load(bani_ctx *ctx, const char *path, bani_index **out);
+/* Contig lengths of the index in seqId order (cap >= n_contigs of bani_index_stats) and the cumulative contig count per
+ * genome (== Sketch::sequencesByFileInfo, winSketch.hpp:75; cap >= n_genomes): what a host needs to rebuild
+ * Sketch::metadata lengths and computeGenomeLengths (computeCoreIdentity.hpp:48-92) for a loaded index. */
+BANI_API int  bani_index_contigs(const bani_index *ix, int32_t *contig_len, uint64_t cap_contigs, int32_t *seqs_by_file, uint64_t cap_genomes);
 
 /* ---- HP2: query mapping ---------------------------------------------------
  * Map::mapQuery (computeMap.hpp:112-196) for one query genome: every mapping the
@@ -199,6 +227,10 @@ BANI_API int  bani_map_cgi(bani_ctx *ctx, const bani_index *ix, bani_genome *con
 typedef struct bani_qsketch bani_qsketch;
 BANI_API int  bani_qsketch_create(bani_ctx *ctx, bani_genome *const *queries, int32_t n_queries, const int32_t *query_ids,
                                   const bani_index *hint, bani_qsketch **out);
+/* The same for genomes OF the index, by genome ordinal, from the index alone (no genome handle, no bases): an index
+ * loaded from disk is also the query side of an all-vs-all run. */
+BANI_API int  bani_qsketch_from_index(bani_ctx *ctx, const bani_index *ix, const int32_t *genome_ordinals, int32_t n_queries,
+                                      const int32_t *query_ids, bani_qsketch **out);
 BANI_API void bani_qsketch_destroy(bani_qsketch *qs);
 BANI_API int  bani_qsketch_info(const bani_qsketch *qs, int32_t *n_queries, uint64_t *n_fragments, uint64_t *n_hashes,
                                 uint64_t *export_bytes);

@@ -179,3 +179,58 @@ def test_cli_writers_format(tmp_path):
             (2, 1, 45, 50, 97.5), (2, 0, 50, 50, 100.0)]
     py = report.output_lines(rows, q, rr, [lens[x] for x in q], [lens[x] for x in rr], 3000, 0.2)
     assert sorted(py) == sorted(open(out).read().splitlines())
+
+
+def test_bench_parity_gate_detects_every_kind_of_difference():
+    """bench.py's parity gate (the rule of tests/fastani_tests.cpp:22-31) on hand-made tables: equal tables pass; a
+    count, a total, an identity beyond 1e-4, a missing row and an extra row are each reported."""
+    import argparse
+    import bench
+    names = ["c0_s0", "c0_s1", "c1_s0"]
+    lens = [4998000] * 3
+    cnt = np.array([[1666, 1500, 0], [1490, 1666, 0], [0, 0, 1666]], np.int32)
+    idn = np.array([[100, 99.2574, 0], [99.25, 100, 0], [0, 0, 100]], np.float32)
+    tot = np.array([1666, 1666, 1666], np.int64)
+    ref = bench.parse_out_txt("/x/c0_s0.fna\t/x/c0_s0.fna\t100\t1666\t1666\n/x/c0_s0.fna\t/x/c0_s1.fna\t99.2574\t1500\t1666\n"
+                              "/y/c1_s0.fna\t/y/c1_s0.fna\t100\t1666\t1666\n")
+    ok = bench.check_parity(ref, [0, 2], [0, 1, 2], names, lens, cnt, idn, tot)
+    assert ok["mismatches"] == 0 and ok["reference_rows"] == 3 and ok["pairs_checked"] == 6
+    for mutate in (lambda c, i, t: c.__setitem__((0, 1), 1499), lambda c, i, t: t.__setitem__(0, 1665),
+                   lambda c, i, t: i.__setitem__((0, 1), 99.2576), lambda c, i, t: c.__setitem__((0, 1), 0),
+                   lambda c, i, t: c.__setitem__((2, 0), 400)):
+        c2, i2, t2 = cnt.copy(), idn.copy(), tot.copy()
+        mutate(c2, i2, t2)
+        bad = bench.check_parity(ref, [0, 2], [0, 1, 2], names, lens, c2, i2, t2)
+        assert bad["mismatches"] >= 1 and bad["example"]
+    # a pair below the --minFraction output filter is not expected in the reference's file
+    c2 = cnt.copy(); c2[2, 0] = 300
+    assert bench.check_parity(ref, [0, 2], [0, 1, 2], names, lens, c2, idn, tot)["mismatches"] == 0
+    cfg = bench.bench_config(argparse.Namespace(clusters=50, strains=20, genome_len=5000000, gpus=4))
+    assert cfg["queries"] == 1000 and "4 GPU" in cfg["parallelism"]
+
+
+def test_host_packer_matches_the_reference_bytes():
+    """bani_pack_contig (no GPU): decoding the 2-bit words and patching the exception list gives back exactly the
+    upper-cased bytes the reference hashes (makeUpperCase touches a-z only, commonFunc.hpp:57-66)."""
+    import pyoracle as po
+    rng = np.random.default_rng(12)
+    seq = bytearray(rng.choice(np.frombuffer(b"ACGTacgt", np.uint8), 100003).tobytes())
+    seq[5:9] = b"NNnn"; seq[40:44] = b"RYkm"; seq[16] = ord("z"); seq[31] = 0xC3; seq[32] = ord("-"); seq[100002] = ord("n")
+    seq[2000:2600] = b"N" * 600
+    cases = [bytes(seq), b"", b"A", b"acgtn", bytes(seq[:16]), bytes(seq[:17]), b"N" * 33]
+    for sq in cases:
+        b = fb.PackedBatch([[("x", sq)]])
+        n = len(sq)
+        codes = ((b.words[:(n + 15) // 16, None] >> (2 * np.arange(16, dtype=np.uint32))) & 3).reshape(-1)[:n]
+        got = np.frombuffer(b"ACGT", np.uint8)[codes].copy()
+        ne = int(b.exc_off[1])
+        got[b.exc_pos[:ne]] = b.exc_byte[:ne]
+        want = po.upper(sq)
+        assert (got == want).all()
+        assert ne == int(np.isin(want, np.frombuffer(b"ACGT", np.uint8), invert=True).sum())
+        assert (np.diff(b.exc_pos[:ne].astype(np.int64)) > 0).all()
+    # several genomes / contigs: 16-byte aligned contig starts, offsets in order; threaded packing gives the same arrays
+    gl = [[("a", cases[0][:5000]), ("b", b""), ("c", cases[0][5000:9001])], [], [("d", b"acgtNNNN")]]
+    b1, b2 = fb.PackedBatch(gl), fb.PackedBatch(gl, threads=3)
+    assert (b1.word_off % 4 == 0).all() and list(b1.gen_off) == [0, 3, 3, 4] and list(b1.contig_len[:4]) == [5000, 0, 4001, 8]
+    assert (b1.words == b2.words).all() and (b1.exc_pos == b2.exc_pos).all() and (b1.exc_off == b2.exc_off).all()
