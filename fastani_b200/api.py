@@ -104,6 +104,7 @@ def load_library():
         "bani_qsketch_info": (C.c_int, [vp, P(i32), P(u64), P(u64), P(u64)]),
         "bani_qsketch_export": (C.c_int, [vp, vp, vp, u64]),
         "bani_qsketch_import": (C.c_int, [vp, vp, u64, P(vp)]),
+        "bani_qsketch_merge": (C.c_int, [vp, P(vp), i32, P(vp)]),
         "bani_map_cgi_sketch": (C.c_int, [vp, vp, P(vp), i32, P(vp), P(u64), P(MapCounters)]),
         "bani_free": (None, [vp]),
         "bani_synth_genome": (C.c_int, [vp, u64, u32, u32, u32, i64, vp]),
@@ -124,7 +125,7 @@ EXPORTED_SYMBOLS = [
     "bani_index_destroy", "bani_index_stats", "bani_index_minimizers", "bani_index_save", "bani_index_load", "bani_index_contigs",
     "bani_qsketch_from_index", "bani_index_lookup", "bani_map_genome",
     "bani_map_cgi", "bani_free", "bani_synth_genome", "bani_qsketch_create", "bani_qsketch_destroy", "bani_qsketch_info",
-    "bani_qsketch_export", "bani_qsketch_import", "bani_map_cgi_sketch"]
+    "bani_qsketch_export", "bani_qsketch_import", "bani_qsketch_merge", "bani_map_cgi_sketch"]
 
 
 def _check(rc):
@@ -519,6 +520,15 @@ class QuerySketch:
     def from_device_buffer(cls, ctx, device_ptr, nbytes):
         h = C.c_void_p()
         _check(ctx.lib.bani_qsketch_import(ctx.h, C.c_void_p(int(device_ptr)), int(nbytes), C.byref(h)))
+        return cls(ctx, _handle=h)
+
+    @classmethod
+    def merge(cls, ctx, sketches):
+        """One sketch holding the queries of `sketches` in order (bani_qsketch_merge); the sources stay valid."""
+        qs = list(sketches)
+        arr = (C.c_void_p * max(len(qs), 1))(*[q.h for q in qs])
+        h = C.c_void_p()
+        _check(ctx.lib.bani_qsketch_merge(ctx.h, arr, len(qs), C.byref(h)))
         return cls(ctx, _handle=h)
 
     def info(self):

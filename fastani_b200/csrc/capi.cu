@@ -144,6 +144,7 @@ int bani_ctx_set_flag(bani_ctx *ctx, const char *name, int64_t value)
   else if (n == "max_hits_per_piece") { if (value < 1) fail(BANI_ERR_ARG, "max_hits_per_piece must be positive"); f.maxHitsPerPiece = value; }
   else if (n == "frag_l1_max") { if (value < 0) fail(BANI_ERR_ARG, "frag_l1_max must not be negative"); f.fragL1Max = value; }
   else if (n == "l2e_buckets") { if (value != 0 && value != 1024 && value != 4096) fail(BANI_ERR_ARG, "l2e_buckets must be 0, 1024 or 4096"); f.l2eBuckets = (int)value; }
+  else if (n == "l2_stage") f.l2Stage = value != 0;
   else if (n == "upload_group_words") { if (value < 1) fail(BANI_ERR_ARG, "upload_group_words must be positive"); f.uploadGroupWords = value; }
   else fail(BANI_ERR_ARG, "unknown flag '%s'", name);
   return BANI_OK;
@@ -512,6 +513,20 @@ int bani_qsketch_import(bani_ctx *ctx, const void *device_buf, uint64_t bytes, b
   BANI_CUDA(cudaSetDevice(ctx->c.device));
   std::unique_ptr<bani_qsketch> h(new bani_qsketch());
   h->qs = qsketch_import(&ctx->c, device_buf, bytes);
+  *out = h.release();
+  return BANI_OK;
+  BANI_CATCH
+}
+
+int bani_qsketch_merge(bani_ctx *ctx, const bani_qsketch *const *sketches, int32_t n_sketches, bani_qsketch **out)
+{
+  BANI_TRY
+  if (!ctx || n_sketches < 0 || (n_sketches && !sketches) || !out) fail(BANI_ERR_ARG, "null argument");
+  BANI_CUDA(cudaSetDevice(ctx->c.device));
+  std::vector<const QSketch *> qs(n_sketches);
+  for (int i = 0; i < n_sketches; i++) { if (!sketches[i] || !sketches[i]->qs) fail(BANI_ERR_ARG, "null query sketch"); qs[i] = sketches[i]->qs; }
+  std::unique_ptr<bani_qsketch> h(new bani_qsketch());
+  h->qs = qsketch_merge(&ctx->c, qs.data(), n_sketches);
   *out = h.release();
   return BANI_OK;
   BANI_CATCH

@@ -194,6 +194,7 @@ struct CtxFlags {
   long long maxHitsPerPiece = 3ll << 29;      // a piece that gathers more index hits is split at a query boundary
   long long fragL1Max = 8192;                 // hits per fragment handled inside one CTA (<= FRAG_L1_MAX)
   int l2eBuckets = 0;                         // 0 = adaptive; 1024 / 4096 force the size of the L2 rank directory
+  int l2Stage = 1;                            // 1: l2_events_kernel stages event codes in shared memory where the window links allow it
   long long uploadGroupWords = 16ll << 20;    // packed words (16 bases each) per upload group of the host-packed ingest
 };
 
@@ -292,6 +293,7 @@ QSketch *qsketch_from_index(Ctx *ctx, const Index *ix, const int32_t *ordinals, 
 uint64_t qsketch_export_bytes(const QSketch *qs);
 void qsketch_export(Ctx *ctx, const QSketch *qs, void *devBuf, uint64_t cap);
 QSketch *qsketch_import(Ctx *ctx, const void *devBuf, uint64_t bytes);
+QSketch *qsketch_merge(Ctx *ctx, const QSketch *const *sketches, int32_t n);
 void qsketch_map(Ctx *ctx, const Index *ix, const QSketch *const *sketches, int32_t nSketches,
                  bool wantRows, bool wantCgi, MapOutput &out);
 

@@ -331,7 +331,7 @@ Index *index_build(Ctx *ctx, Genome *const *refs, int32_t nRefs)
       int32_t c = 0;
       for (int g = 0; g < nRefs; g++) {
         const Genome *G = refs[g];
-        const bool newGroup = groups.empty() || !G->blk || G->blk != groupHead.back()->blk;
+        const bool newGroup = groups.empty() || G->blk != groupHead.back()->blk;       // genomes with their own buffers (no block) share one group
         if (newGroup) { groups.push_back({c, c}); groupHead.push_back(G); }
         c += G->nContigs; groups.back().second = c;
       }

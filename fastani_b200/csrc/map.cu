@@ -45,13 +45,14 @@ static constexpr int SU_CAP = 4096;
 
 __global__ void __launch_bounds__(SU_THREADS)
 sort_unique_kernel(uint32_t *fragHash, const uint32_t *segStart, int32_t F, int32_t *sCount,
-                   int *smax, int *err)
+                   int *smax, int *err, int minN /* fragments of at most this many raw minimizers are skipped */)
 {
   __shared__ uint32_t a[SU_CAP];
   __shared__ uint32_t wsum[SU_THREADS / 32];
   const int f = blockIdx.x, tid = threadIdx.x;
   const uint32_t beg = segStart[f];
   const int n = (int)(segStart[f + 1] - beg);
+  if (n <= minN) return;                                   // done by sort_unique_warp_kernel
   if (n > SU_CAP) { if (tid == 0) { atomicExch(err, 1); sCount[f] = 0; } return; }
   if (n == 0) { if (tid == 0) sCount[f] = 0; return; }
   int n2 = 1; while (n2 < n) n2 <<= 1;
@@ -83,6 +84,48 @@ sort_unique_kernel(uint32_t *fragHash, const uint32_t *segStart, int32_t F, int3
   uint32_t o = base + incl - cnt;
   for (int i = i0; i < i1; i++) if (i == 0 || a[i] != a[i - 1]) fragHash[beg + o++] = a[i];
   if (tid == 0) { sCount[f] = (int32_t)total; atomicMax(smax, (int)total); }
+}
+
+// Warp per fragment for the common sizes (<= 512 raw minimizers: every default parameter set): the same bitonic network in
+// a 2 KB slice of shared memory, warp-synchronous (no block barrier per sub-stage), unique + count by ballots.  Larger
+// fragments are counted in *nBig and left to the CTA kernel above.
+static constexpr int SUW_CAP = 512;
+static constexpr int SUW_WARPS = 4;
+
+__global__ void __launch_bounds__(SUW_WARPS * 32)
+sort_unique_warp_kernel(uint32_t *fragHash, const uint32_t *segStart, int32_t F, int32_t *sCount, int *smax, int *nBig)
+{
+  __shared__ uint32_t sm[SUW_WARPS][SUW_CAP];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int f = blockIdx.x * SUW_WARPS + wid;
+  if (f >= F) return;
+  uint32_t *a = sm[wid];
+  const uint32_t beg = segStart[f];
+  const int n = (int)(segStart[f + 1] - beg);
+  if (n > SUW_CAP) { if (lane == 0) atomicAdd(nBig, 1); return; }
+  if (n == 0) { if (lane == 0) sCount[f] = 0; return; }
+  int n2 = 32; while (n2 < n) n2 <<= 1;
+  for (int i = lane; i < n2; i += 32) a[i] = i < n ? fragHash[beg + i] : 0xFFFFFFFFu;
+  __syncwarp();
+  for (int k2 = 2; k2 <= n2; k2 <<= 1)
+    for (int j = k2 >> 1; j > 0; j >>= 1) {
+      for (int t = lane; t < (n2 >> 1); t += 32) {          // pair t: the lower index has bit j clear
+        const int i = 2 * t - (t & (j - 1)), p = i + j;
+        const uint32_t x = a[i], y = a[p];
+        const bool asc = (i & k2) == 0;
+        if ((x > y) == asc) { a[i] = y; a[p] = x; }
+      }
+      __syncwarp();
+    }
+  uint32_t run = 0;
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    const int i = i0 + lane;
+    const bool head = i < n && (i == 0 || a[i] != a[i - 1]);
+    const uint32_t bal = __ballot_sync(0xffffffffu, head);
+    if (head) fragHash[beg + run + __popc(bal & ((1u << lane) - 1u))] = a[i];
+    run += __popc(bal);
+  }
+  if (lane == 0) { sCount[f] = (int32_t)run; atomicMax(smax, (int)run); }
 }
 
 // ------------------------------------------------------------------ C: lookup
@@ -323,9 +366,9 @@ static constexpr int L2_SHM_BUDGET = 200 * 1024;      // dynamic shared memory g
 static constexpr uint32_t EV_M = 1u, EV_D = 2u, EV_S = 4u, EV_JMASK = 0xFFE0u;
 __host__ __device__ __forceinline__ uint32_t ev_rank(uint32_t j) { return j << 5; }
 
-static constexpr int L2E_RING = 2048;             // events staged per warp of l2_events_kernel (4 KB)
-static constexpr int L2E_FLUSH_IT = 8;            // iterations of 32 records between two flushes = 32 steps of 16 events, one per lane
-static constexpr int L2E_BF_MAX = L2E_RING - 64 * L2E_FLUSH_IT - 96;   // 1440: largest (max back + max fwd) of a staged candidate
+static constexpr int L2E_RING = 1024;             // events staged per warp of l2_events_kernel (2 KB: 6 CTAs of 8 warps per SM)
+static constexpr int L2E_FLUSH_IT = 4;            // iterations of 32 records between two flushes = 16 steps of 16 events
+static constexpr int L2E_BF_MAX = L2E_RING - 64 * L2E_FLUSH_IT - 96;   // 672: largest (max back + max fwd) of a staged candidate
 
 struct L2PArgs {
   const int32_t *cFrag, *cSeq, *cStart, *cEnd; uint32_t C;
@@ -334,6 +377,7 @@ struct L2PArgs {
   const uint4 *rec; const int32_t *recWposSoA; const uint32_t *contigRecOff;
   const uint2 *rec8; const uint32_t *recLink; const uint32_t *blkMax;      // compact L2 records + per-1024-record link bounds (index.cu)
   int fragLen, cmw, sLimit, shiftA, nBuckets;      // nBuckets: 1024 or 4096 (power of two), directory over h >> shiftA
+  int stage;                                       // 0: every candidate takes the direct-store path of l2_events_kernel (switch "l2_stage")
   uint32_t *cB0, *cE0, *cLast, *cNEv, *cChunks;   // per candidate
   uint16_t *cMB;                                   // per candidate: bound on `back` of its records when its events can be staged, else 0xFFFF
   const uint32_t *cOff;                            // first 32-byte slot of the candidate's stream; step k is slot cOff + 32 * k
@@ -389,7 +433,7 @@ __global__ void l2_bounds_kernel(const L2PArgs a)
         const uint32_t blk1 = (last - 1) >> 10;
         for (uint32_t blk = b0 >> 10; blk <= blk1 && mbk != 0xFFFFu; blk++) { const uint32_t v = __ldg(&a.blkMax[blk]); mbk = max(mbk, v & 0xFFFFu); mfw = max(mfw, v >> 16); }
       }
-      a.cMB[c] = (uint16_t)((mbk + mfw <= (uint32_t)L2E_BF_MAX) ? mbk : 0xFFFFu);
+      a.cMB[c] = (uint16_t)((a.stage && mbk + mfw <= (uint32_t)L2E_BF_MAX) ? mbk : 0xFFFFu);
     }
     a.cNEv[c] = fast ? nEv : 0u;
     a.cChunks[c] = fast ? (nEv + 15) >> 4 : 0u;      // 32-byte steps of 16 events
@@ -1051,11 +1095,15 @@ static QSketch *qsketch_build(Ctx *ctx, const std::vector<QuerySrc> &srcs, const
 
       // ---- B: sorted unique hashes per fragment, then packed back to back
       pc->sCount.alloc(F, st); pc->segStart.alloc((size_t)F + 1, st);
-      DevBuf<int> d_flags(2, st);
-      BANI_CUDA(cudaMemsetAsync(d_flags.p, 0, 8, st));
+      DevBuf<int> d_flags(4, st);
+      BANI_CUDA(cudaMemsetAsync(d_flags.p, 0, 16, st));
       unsigned long long T2 = 0;
       { Stage sg(ctx, "q_sort_unique", 8.0 * T);
-        sort_unique_kernel<<<F, SU_THREADS, 0, st>>>(rawHash.p, rawStart.p, F, pc->sCount.p, d_flags.p, d_flags.p + 1); ctx->launches++;
+        sort_unique_warp_kernel<<<nblk(F, SUW_WARPS), SUW_WARPS * 32, 0, st>>>(rawHash.p, rawStart.p, F, pc->sCount.p, d_flags.p, d_flags.p + 2); ctx->launches++;
+        int nBig = 0;
+        BANI_CUDA(cudaMemcpyAsync(&nBig, d_flags.p + 2, 4, cudaMemcpyDeviceToHost, st));
+        BANI_CUDA(cudaStreamSynchronize(st));
+        if (nBig > 0) { sort_unique_kernel<<<F, SU_THREADS, 0, st>>>(rawHash.p, rawStart.p, F, pc->sCount.p, d_flags.p, d_flags.p + 1, SUW_CAP); ctx->launches++; }
         BANI_SCRATCH(uint32_t, cnt1, (size_t)F + 1);
         BANI_CUDA(cudaMemcpyAsync(cnt1.p, pc->sCount.p, 4 * (size_t)F, cudaMemcpyDeviceToDevice, st));
         BANI_CUDA(cudaMemsetAsync(cnt1.p + F, 0, 4, st));
@@ -1217,6 +1265,63 @@ __global__ void rebase_u32_kernel(const uint32_t *in, uint32_t delta, uint64_t n
 {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = in[i] - delta;
+}
+
+// ---- several sketches as one: the pieces are packed back to back into pieces of up to FRAG_MAX fragments, so that
+//      the sketches a rank received from its peers are mapped in a few large passes instead of one small pass per peer
+QSketch *qsketch_merge(Ctx *ctx, const QSketch *const *sketches, int32_t n)
+{
+  cudaStream_t st = ctx->stream;
+  auto out = std::make_unique<QSketch>();
+  out->device = ctx->device; out->k = ctx->prm.kmer_size; out->w = ctx->prm.window_size; out->fragLen = ctx->prm.frag_len;
+  struct Src { const QPiece *pc; int qBase; };
+  std::vector<Src> srcs;
+  for (int i = 0; i < n; i++) {
+    const QSketch *qs = sketches[i];
+    if (!qs) fail(BANI_ERR_ARG, "null query sketch");
+    if (qs->device != ctx->device) fail(BANI_ERR_ARG, "query sketch lives on another device");
+    if (qs->k != out->k || qs->w != out->w || qs->fragLen != out->fragLen) fail(BANI_ERR_ARG, "query sketch was built with other parameters");
+    const int qBase = (int)out->queryId.size();
+    out->queryId.insert(out->queryId.end(), qs->queryId.begin(), qs->queryId.end());
+    out->totalFragments.insert(out->totalFragments.end(), qs->totalFragments.begin(), qs->totalFragments.end());
+    for (const auto &pc : qs->pieces) srcs.push_back(Src{pc.get(), qBase + pc->q0});
+  }
+  size_t i = 0;
+  while (i < srcs.size()) {
+    size_t j = i; uint64_t F = 0, T = 0;
+    while (j < srcs.size() && (j == i || (F + (uint64_t)srcs[j].pc->F <= FRAG_MAX && T + srcs[j].pc->T < 0xfffffff0ull &&
+                                          srcs[j].qBase == srcs[j - 1].qBase + srcs[j - 1].pc->nq))) { F += (uint64_t)srcs[j].pc->F; T += srcs[j].pc->T; j++; }
+    auto pc = std::make_unique<QPiece>();
+    pc->q0 = srcs[i].qBase; pc->F = (int32_t)F; pc->T = T;
+    if (F > 0) {
+      pc->segStart.alloc((size_t)F + 1, st); pc->sCount.alloc(F, st); pc->fragQuery.alloc(F, st); pc->fragSeqId.alloc(F, st);
+      pc->fragHash.alloc(std::max<uint64_t>(T, 1), st);
+    }
+    uint64_t fo = 0, to = 0; int qo = 0;
+    for (size_t s = i; s < j; s++) {
+      const QPiece &sp = *srcs[s].pc;
+      for (int q = 0; q < sp.nq; q++) pc->qFragOff.push_back(sp.qFragOff[q] + (int32_t)fo);
+      pc->smax = std::max(pc->smax, sp.smax);
+      if (sp.F > 0) {
+        const size_t sf = (size_t)sp.F;
+        rebase_u32_kernel<<<nblk(sf + 1), 256, 0, st>>>(sp.segStart.p, (uint32_t)(0u - (uint32_t)to), sf + 1, pc->segStart.p + fo);
+        rebase_u32_kernel<<<nblk(sf), 256, 0, st>>>((const uint32_t *)sp.fragQuery.p, (uint32_t)(0u - (uint32_t)qo), sf, (uint32_t *)pc->fragQuery.p + fo);
+        ctx->launches += 2;
+        BANI_CUDA(cudaMemcpyAsync(pc->sCount.p + fo, sp.sCount.p, 4 * sf, cudaMemcpyDeviceToDevice, st));
+        BANI_CUDA(cudaMemcpyAsync(pc->fragSeqId.p + fo, sp.fragSeqId.p, 4 * sf, cudaMemcpyDeviceToDevice, st));
+        if (sp.T) BANI_CUDA(cudaMemcpyAsync(pc->fragHash.p + to, sp.fragHash.p, 4 * sp.T, cudaMemcpyDeviceToDevice, st));
+      }
+      fo += (uint64_t)sp.F; to += sp.T; qo += sp.nq;
+    }
+    pc->nq = qo;
+    pc->qFragOff.push_back((int32_t)F);
+    out->F += F; out->T += T;
+    out->pieces.push_back(std::move(pc));
+    i = j;
+  }
+  BANI_CUDA(cudaGetLastError());
+  BANI_CUDA(cudaStreamSynchronize(st));          // the sources may be destroyed when this returns
+  return out.release();
 }
 
 static std::unique_ptr<QPiece> slice_piece(Ctx *ctx, const QPiece &pc, int qa, int qb)
@@ -1440,7 +1545,7 @@ void qsketch_map(Ctx *ctx, const Index *ix, const QSketch *const *sketches, int3
               L2PArgs lp; lp.cFrag = cFrag.p; lp.cSeq = cSeq.p; lp.cStart = cStart.p; lp.cEnd = cEnd.p; lp.C = C;
               lp.fragCandOff = fragCandOff.p; lp.fragHash = fragHash.p; lp.segStart = segStart.p; lp.sCount = sCount.p;
               lp.rec = ix->rec.p; lp.recWposSoA = ix->wpos.p; lp.contigRecOff = ix->contigRecOff.p; lp.fragLen = fragLen; lp.cmw = cmw;
-              lp.rec8 = ix->rec8.p; lp.recLink = ix->link.p; lp.blkMax = ix->blkMax.p;
+              lp.rec8 = ix->rec8.p; lp.recLink = ix->link.p; lp.blkMax = ix->blkMax.p; lp.stage = ctx->flags.l2Stage;
               // fast path: needs the window links of the index (cmw >= 2) and ranks that fit the event code
               // (and whose per-warp state fits the shared-memory budget of l2_seq_kernel: larger sketches take l2_kernel)
               lp.sLimit = (cmw >= 2 && ix->cmw == cmw && ix->rec8.p) ? std::min(std::min(smax, L2_SMAX), L2_SHM_BUDGET / (L2S_WARPS * 32) - 2) : 0;

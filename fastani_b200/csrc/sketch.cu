@@ -284,7 +284,19 @@ sketch_kernel(const SketchArgs a)
 
   // ---- phase 4: emission flags
   uint32_t emit = 0;
-  {
+  // Common case: all 16 positions of the thread and the slot before them are valid, so the previous valid position of
+  // every position is simply its left neighbour and the window minima are still in registers: m(i) != m(i-1)
+  // (position w-1, the first complete window, always emits).  Anything else takes the general search below.
+  const bool fastEmit = w >= 2 && vmask == 0xFFFFu && q0 > 0 && ((s_vmask[(q0 - 1) >> 4] >> ((q0 - 1) & 15)) & 1u);
+  if (fastEmit) {
+    uint64_t prev = s_key[KIDX(q0 - 1)];
+#pragma unroll
+    for (int j = 0; j < SK_P; j++) {
+      const int p = hs + q0 + j;
+      if (p >= t0 && p >= w - 1 && (p == w - 1 || M[j] != prev)) emit |= 1u << j;
+      prev = M[j];
+    }
+  } else {
 #pragma unroll 1
     for (uint32_t vm = vmask; vm; vm &= vm - 1) {
       const int j = __ffs(vm) - 1;

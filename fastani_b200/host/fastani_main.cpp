@@ -19,6 +19,7 @@
 #include <mutex>
 #include <sstream>
 #include <thread>
+#include <unistd.h>
 #include "ani_host.hpp"
 
 using namespace skch;
@@ -187,6 +188,7 @@ int main(int argc, char **argv)
     cgi::outputPhylip(p, len, v, argv[2]);
     return 0;
   }
+  const auto tStart = Clock::now();
   Parameters parameters;
   parseandSave(argc, argv, parameters);
   const std::string fileName = parameters.outFileName;
@@ -200,11 +202,24 @@ int main(int argc, char **argv)
                                  ", this run asks for k " + std::to_string(parameters.kmerSize) + " fragLen " + std::to_string(parameters.minReadLength) + " window " + std::to_string(parameters.windowSize));
       parameters.refSequences = meta.refPaths;
     }
+    // a run that names its GPU count initialises only those devices (the driver's start-up cost grows with every visible GPU)
+    {
+      const int want = loading ? meta.shards : parameters.gpus;
+      if (want > 0 && !getenv("CUDA_VISIBLE_DEVICES")) {
+        std::string v; for (int g = 0; g < want; g++) v += (g ? "," : "") + std::to_string(g);
+        setenv("CUDA_VISIBLE_DEVICES", v.c_str(), 0);
+      }
+    }
     int32_t nDev = 0;
     if (bani_device_count(&nDev) != BANI_OK || nDev == 0) throw std::runtime_error("no CUDA device available (this program has no CPU path)");
     const int G = loading ? meta.shards : (parameters.gpus > 0 ? std::min(parameters.gpus, nDev) : nDev);
     if (G > nDev) throw std::runtime_error("the saved index has " + std::to_string(G) + " shards but only " + std::to_string(nDev) + " GPU(s) are visible");
     const auto shards = cgi::splitReferenceGenomes((int)parameters.refSequences.size(), G);
+    // the contexts (CUDA context creation, stream set-up) come up while the reader threads parse and pack the files
+    std::vector<bani_ctx *> ctxs(G, nullptr); std::vector<std::string> ctxErr(G);
+    std::vector<std::thread> ctxThreads;
+    for (int g = 0; g < G; g++)
+      ctxThreads.emplace_back([&, g]() { bani_params cp = parameters.c(); if (bani_ctx_create(g, &cp, &ctxs[g]) != BANI_OK) ctxErr[g] = bani_last_error(); });
 
     // ---- ingest: every distinct file once, in parallel.  With a loaded index no reference file is read, and (one
     //      shard, no --visualize) neither is a query that is a genome of the index: its sketch is derived from the index
@@ -228,12 +243,14 @@ int main(int argc, char **argv)
       std::vector<std::thread> th;
       for (int i = 0; i < std::min<int>(parameters.threads, (int)paths.size()); i++) th.emplace_back(work);
       for (auto &t : th) t.join();
+      for (auto &t : ctxThreads) t.join();
       if (!err.empty()) throw std::runtime_error(err);
     }
     std::unordered_map<std::string, uint64_t> genomeLengths;
     for (size_t i = 0; i < paths.size(); i++) genomeLengths[paths[i]] = cgi::genomeLength(genomes[i], parameters.minReadLength);
     std::cerr << "INFO, skch::main, Time spent reading " << paths.size() << " genome files : "
               << std::chrono::duration<double>(Clock::now() - t0).count() << " sec" << std::endl;
+    for (int g = 0; g < G; g++) if (!ctxs[g]) throw std::runtime_error("bani_ctx_create: " + ctxErr[g]);
 
     std::vector<cgi::CGI_Results> finalResults;
     std::vector<std::string> visual(G);
@@ -244,9 +261,7 @@ int main(int argc, char **argv)
     auto shardWork = [&](int g) {
       try {
         auto t1 = Clock::now();
-        bani_params cp = parameters.c();
-        bani_ctx *ctx = nullptr;
-        check(bani_ctx_create(g, &cp, &ctx), "bani_ctx_create");
+        bani_ctx *ctx = ctxs[g];
         {
           // genomes this device needs: its reference shard (unless loaded) and every query that has to be read, each file once
           std::vector<int> need; std::unordered_map<int, int> slot;
@@ -320,7 +335,7 @@ int main(int argc, char **argv)
           std::lock_guard<std::mutex> l(mu);
           finalResults.insert(finalResults.end(), local.begin(), local.end());
         }
-        bani_ctx_destroy(ctx);
+        if (getenv("BANI_CLI_FULL_TEARDOWN")) bani_ctx_destroy(ctx);      // otherwise the process exit returns the device memory (faster)
       } catch (const std::exception &e) { std::lock_guard<std::mutex> l(mu); err = e.what(); }
     };
     {
@@ -338,9 +353,12 @@ int main(int argc, char **argv)
     cgi::outputCGI(parameters, genomeLengths, finalResults, fileName);
     if (parameters.matrixOutput) cgi::outputPhylip(parameters, genomeLengths, finalResults, fileName);
     if (parameters.visualize) { std::ofstream o(fileName + ".visual"); for (int g = 0; g < G; g++) o << visual[g]; }
+    std::cerr << "INFO, skch::main, Total time : " << std::chrono::duration<double>(Clock::now() - tStart).count() << " sec" << std::endl;
   } catch (const std::exception &e) {
     std::cerr << "ERROR, " << e.what() << std::endl;
     return 1;
   }
+  std::cout.flush(); std::cerr.flush();
+  if (!getenv("BANI_CLI_FULL_TEARDOWN")) _exit(0);      // outputs are written and closed: skip the destructors of multi-GB host tables and the CUDA teardown
   return 0;
 }

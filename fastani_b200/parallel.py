@@ -78,28 +78,48 @@ def gather_tables(cnt_local, idn_local, n_refs, world, rank, dist=None, device=N
     return merge_shards(tables, n_queries, n_refs, world)
 
 
+class SketchExchange:
+    """An all-gather of the ranks' QuerySketch objects in flight (start_exchange ... finish)."""
+
+    def __init__(self, ctx, mine, world, rank, dist, device, importer=None):
+        import torch
+        if importer is None:
+            from .api import QuerySketch
+            importer = QuerySketch.from_device_buffer
+        self.ctx, self.mine, self.world, self.rank, self.device, self.importer = ctx, mine, world, rank, device, importer
+        nbytes = mine.info()["export_bytes"]
+        sizes = torch.zeros(world, dtype=torch.int64, device=device)
+        sizes[rank] = nbytes
+        dist.all_reduce(sizes)
+        self.sizes = [int(x) for x in sizes.cpu()]
+        self.width = (max(self.sizes) + 255) // 256 * 256
+        self.send = torch.empty(self.width, dtype=torch.uint8, device=device)
+        mine.export_to(self.send.data_ptr(), self.width)    # synchronises the library's stream: the bytes are in place
+        self.recv = torch.empty(world * self.width, dtype=torch.uint8, device=device)
+        self.work = dist.all_gather_into_tensor(self.recv, self.send, async_op=True)
+
+    def finish(self):
+        """Waits for the collective and rebuilds the peers' sketches on this device (bani_qsketch_import).
+        Returns the `world` sketches in rank order (this rank's own object included)."""
+        import torch
+        self.work.wait()
+        if getattr(self.device, "type", str(self.device)) != "cpu":
+            torch.cuda.synchronize(self.device)
+        out = []
+        for r in range(self.world):
+            out.append(self.mine if r == self.rank else self.importer(self.ctx, self.recv.data_ptr() + r * self.width, self.sizes[r]))
+        return out
+
+
+def start_exchange(ctx, mine, world, rank, dist, device, importer=None):
+    """Export this rank's QuerySketch into a flat device buffer and START the padded all-gather (NCCL over NVLink on GPUs);
+    the caller maps its own sketch against its shard while the peers' sketches travel, then calls .finish()."""
+    return SketchExchange(ctx, mine, world, rank, dist, device, importer)
+
+
 def exchange_query_sketches(ctx, mine, world, rank, dist, device, importer=None):
     """All-gather of the ranks' QuerySketch objects: each is packed into a flat device buffer (bani_qsketch_export),
     the buffers travel in one padded NCCL all-gather, and the peers' sketches are rebuilt on this device
     (bani_qsketch_import).  Returns the `world` sketches in rank order (this rank's own object included).
     `importer(ctx, ptr, nbytes)` defaults to QuerySketch.from_device_buffer (the CPU/gloo test passes a stand-in)."""
-    import torch
-    if importer is None:
-        from .api import QuerySketch
-        importer = QuerySketch.from_device_buffer
-    nbytes = mine.info()["export_bytes"]
-    sizes = torch.zeros(world, dtype=torch.int64, device=device)
-    sizes[rank] = nbytes
-    dist.all_reduce(sizes)
-    sizes = [int(x) for x in sizes.cpu()]
-    width = (max(sizes) + 255) // 256 * 256
-    send = torch.empty(width, dtype=torch.uint8, device=device)
-    mine.export_to(send.data_ptr(), width)              # synchronises the library's stream: the bytes are in place
-    recv = torch.empty(world * width, dtype=torch.uint8, device=device)
-    dist.all_gather_into_tensor(recv, send)
-    if getattr(device, "type", str(device)) != "cpu":
-        torch.cuda.synchronize(device)
-    out = []
-    for r in range(world):
-        out.append(mine if r == rank else importer(ctx, recv.data_ptr() + r * width, sizes[r]))
-    return out
+    return start_exchange(ctx, mine, world, rank, dist, device, importer).finish()

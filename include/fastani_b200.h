@@ -116,7 +116,7 @@ BANI_API void *bani_ctx_stream(bani_ctx *ctx);
 
 /* Run-time switches of a context.  name: "sketch_reuse" (1 = read the fragment sketches of index members from the
  * index, 0 = always hash the query fragments: what a run with --ql != --rl does), "max_hits_per_piece",
- * "frag_l1_max", "l2e_buckets", "upload_group_words" (tuning / test switches; results never depend on them). */
+ * "frag_l1_max", "l2e_buckets", "l2_stage", "upload_group_words" (tuning / test switches; results never depend on them). */
 BANI_API int  bani_ctx_set_flag(bani_ctx *ctx, const char *name, int64_t value);
 
 /* Per-stage device timing.  When enabled, every stage of HP1/HP2 is bracketed by CUDA events on
@@ -237,6 +237,9 @@ BANI_API int  bani_qsketch_info(const bani_qsketch *qs, int32_t *n_queries, uint
 /* Pack into / rebuild from one flat DEVICE buffer (cap >= export_bytes; 16-byte aligned). */
 BANI_API int  bani_qsketch_export(bani_ctx *ctx, const bani_qsketch *qs, void *device_buf, uint64_t cap);
 BANI_API int  bani_qsketch_import(bani_ctx *ctx, const void *device_buf, uint64_t bytes, bani_qsketch **out);
+/* Several sketches of this device as ONE (queries in the order given; the sources stay valid and may be destroyed): the
+ * sketches a rank received from its peers are then mapped in a few large passes instead of one small pass per peer. */
+BANI_API int  bani_qsketch_merge(bani_ctx *ctx, const bani_qsketch *const *sketches, int32_t n_sketches, bani_qsketch **out);
 /* bani_map_cgi for prebuilt sketches (all on this context's device); results ordered by (sketch, query, refGenomeId). */
 BANI_API int  bani_map_cgi_sketch(bani_ctx *ctx, const bani_index *ix, const bani_qsketch *const *sketches, int32_t n_sketches,
                                   bani_cgi_result **results, uint64_t *n_results, bani_map_counters *counters);

@@ -344,6 +344,12 @@ def test_query_sketch_objects_export_import_and_map():
     key = lambda a: np.sort(a, order=["qryGenomeId", "refGenomeId"])
     assert key(got).tobytes() == key(want).tobytes()
     assert ctr2.as_dict() == ctr.as_dict()
+    # merged sketches (what a rank does with the sketches of its peers): same rows, in the order given
+    m = fb.QuerySketch.merge(ctx, [s1b, s0])
+    assert m.info()["n_queries"] == n and m.info()["n_fragments"] == int(tot.sum())
+    got2, ctr3 = fb.compute_cgi_sketched(ctx, sk, [m])
+    assert key(got2).tobytes() == key(want).tobytes() and ctr3.as_dict() == ctr.as_dict()
+    assert [int(x) for x in got2["qryGenomeId"][:1]] == [odd[0]] or len(got2) == 0
     # truncated / foreign buffers are rejected
     with pytest.raises(fb.BaniError):
         fb.QuerySketch.from_device_buffer(ctx, buf.data_ptr(), 32)

@@ -10,6 +10,9 @@ strains = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 L = int(sys.argv[3]) if len(sys.argv) > 3 else 5_000_000
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 2
 ctx = fb.Context(fb.Parameters())
+for kv in sys.argv[5:]:                       # run-time switches, e.g. l2_stage=0
+    k_, v_ = kv.split("=")
+    ctx.set_flag(k_, int(v_))
 nG = clusters * strains
 host = ctx.pinned(nG * L)
 for g in range(nG):
