@@ -92,6 +92,7 @@ int bani_ctx_create(int device, const bani_params *p, bani_ctx **out)
     if (getenv("BANI_NO_SKETCH_REUSE")) f.sketchReuse = 0;
     if (const char *e = getenv("BANI_MAX_HITS_PER_PIECE")) f.maxHitsPerPiece = std::max(1ll, atoll(e));
     if (const char *e = getenv("BANI_FRAG_L1_MAX")) f.fragL1Max = std::max(0ll, atoll(e));
+    if (const char *e = getenv("BANI_L2_STAGE")) f.l2Stage = atoi(e) != 0;
     if (const char *e = getenv("BANI_L2E_BUCKETS")) { const int v = atoi(e); if (v == 1024 || v == 4096) f.l2eBuckets = v; }
   }
   dev_cache_flush(device);                   // blocks cached under streams of destroyed contexts

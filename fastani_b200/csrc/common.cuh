@@ -71,8 +71,10 @@ struct StatLut {
   std::vector<int32_t> minHits;     // index s (0 unused)
   std::vector<uint32_t> rowOff;     // index s -> offset into ident/upper
   std::vector<float> ident, upper;
-  int smax = 0;
-  void ensure(int s_needed);        // extends rows up to s_needed (host)
+  int smax = 0;                     // rows 1 .. smax are all present (dense part)
+  std::vector<char> have;           // beyond the dense part: rows computed on demand (index s)
+  void ensure(int s_needed);        // extends the dense part up to s_needed (host)
+  bool ensure_rows(const std::vector<int> &svals);   // makes the rows of these sketch sizes present; true if anything was added
 };
 
 // ---------------------------------------------------------------- genomes
@@ -188,13 +190,14 @@ struct View {
 };
 
 // Run-time switches of a context (bani_ctx_set_flag); the defaults can also be set through the environment
-// (BANI_NO_SKETCH_REUSE, BANI_MAX_HITS_PER_PIECE, BANI_FRAG_L1_MAX, BANI_L2E_BUCKETS), read when the context is created.
+// (BANI_NO_SKETCH_REUSE, BANI_MAX_HITS_PER_PIECE, BANI_FRAG_L1_MAX, BANI_L2E_BUCKETS, BANI_L2_STAGE), read when the context is created.
 struct CtxFlags {
   int sketchReuse = 1;                        // stage A': fragment sketches of index members are read from the index
   long long maxHitsPerPiece = 3ll << 29;      // a piece that gathers more index hits is split at a query boundary
   long long fragL1Max = 8192;                 // hits per fragment handled inside one CTA (<= FRAG_L1_MAX)
   int l2eBuckets = 0;                         // 0 = adaptive; 1024 / 4096 force the size of the L2 rank directory
-  int l2Stage = 1;                            // 1: l2_events_kernel stages event codes in shared memory where the window links allow it
+  int l2Stage = 0;                            // 1: l2_events_kernel stages event codes in shared memory where the window links allow it
+                                              //    (measured slower than the direct stores on B200: DESIGN.md section 6; kept as a tested alternative)
   long long uploadGroupWords = 16ll << 20;    // packed words (16 bases each) per upload group of the host-packed ingest
 };
 
@@ -208,7 +211,7 @@ struct Ctx {
   StatLut lut;
   DevBuf<int32_t> d_minHits; DevBuf<uint32_t> d_rowOff; DevBuf<float> d_ident, d_upper;
   int lutUploaded = 0;
-  void upload_lut(int smax);
+  void upload_lut(int smax, const int32_t *d_sCount = nullptr, int32_t F = 0);
   // optional per-stage device timing (CUDA events on `stream`), see bani_ctx_profile_*
   uint64_t launches = 0;             // kernels of this library launched so far (CUB's not counted)
   bool profiling = false;

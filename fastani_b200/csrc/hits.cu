@@ -41,7 +41,7 @@ __global__ void frag_classify_kernel(const uint32_t *segStart, const unsigned lo
 }
 
 // Block-wide stable LSD radix sort of CAP = 256 * ITEMS 32-bit keys held in shared memory, DB bits per pass (8 for the
-// small classes, 10 for the others: a 29-bit record index takes 3 passes instead of 4).
+// classes up to 2048 hits, 10 for the larger ones: a 29-bit record index then takes 3 passes instead of 4).
 // Warp w owns the keys [w * 32 * ITEMS, (w+1) * 32 * ITEMS) of the current order and ranks them round by round
 // (32 consecutive keys per round): lanes with the same digit find each other with match.any, the lowest of them
 // bumps the warp's digit counter once for the whole group, the others take their place from the lane order --
@@ -106,7 +106,9 @@ __device__ __forceinline__ uint32_t *block_radix_sort(uint32_t *in, uint32_t *ou
   return in;
 }
 
-template <int ITEMS> struct FragSortBits { static constexpr int DB = ITEMS >= 3 ? 10 : 8; };
+// 10-bit digits save a pass (3 instead of 4 for a 29-bit record index) but quadruple the per-pass fixed cost (zeroing and
+// scanning 8 per-warp histograms): measured break-even at ~8 keys per thread
+template <int ITEMS> struct FragSortBits { static constexpr int DB = ITEMS >= 10 ? 10 : 8; };
 
 template <int ITEMS>
 __global__ void __launch_bounds__(256)

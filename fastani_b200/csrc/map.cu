@@ -841,12 +841,39 @@ __global__ void cgi_sum_kernel(uint32_t *table, uint8_t *touched, const uint32_t
 }
 
 // ------------------------------------------------------------------ host orchestration
-void Ctx::upload_lut(int smaxNeeded)
+__global__ void scount_present_kernel(const int32_t *sCount, int32_t F, int smax, uint32_t *present)
+{
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= F) return;
+  const int s = sCount[f];
+  if (s >= 1 && s <= smax) present[s] = 1u;
+}
+
+// The (s, shared) tables of stats.cpp on the device.  Sketch sizes up to LUT_DENSE get every row; beyond that (tiny
+// windows: thousands of minimizers per fragment, a row costs O(s^2)) only the sizes that occur in the piece.
+static constexpr int LUT_DENSE = 400;
+void Ctx::upload_lut(int smaxNeeded, const int32_t *d_sCount, int32_t F)
 {
   lut.k = prm.kmer_size; lut.pid = prm.perc_identity;
-  if (smaxNeeded <= lutUploaded && lutUploaded > 0) return;
-  int target = std::max(smaxNeeded, 320);
-  lut.ensure(target);
+  bool changed = false;
+  const int dense = std::min(std::max(smaxNeeded, 320), LUT_DENSE);
+  if (lut.smax < dense) { lut.ensure(dense); changed = true; }
+  if (smaxNeeded > LUT_DENSE) {
+    if (!d_sCount) { lut.ensure(smaxNeeded); changed = true; }          // no size list: every row
+    else {
+      DevBuf<uint32_t> present((size_t)smaxNeeded + 1, stream);
+      BANI_CUDA(cudaMemsetAsync(present.p, 0, 4 * ((size_t)smaxNeeded + 1), stream));
+      scount_present_kernel<<<nblk(F), 256, 0, stream>>>(d_sCount, F, smaxNeeded, present.p);
+      launches++;
+      std::vector<uint32_t> h((size_t)smaxNeeded + 1);
+      BANI_CUDA(cudaMemcpyAsync(h.data(), present.p, 4 * h.size(), cudaMemcpyDeviceToHost, stream));
+      BANI_CUDA(cudaStreamSynchronize(stream));
+      std::vector<int> svals;
+      for (int sv = LUT_DENSE + 1; sv <= smaxNeeded; sv++) if (h[sv]) svals.push_back(sv);
+      changed |= lut.ensure_rows(svals);
+    }
+  }
+  if (!changed && lutUploaded > 0) return;
   d_minHits.alloc(lut.minHits.size(), stream); d_rowOff.alloc(lut.rowOff.size(), stream);
   d_ident.alloc(lut.ident.size(), stream); d_upper.alloc(lut.upper.size(), stream);
   BANI_CUDA(cudaMemcpyAsync(d_minHits.p, lut.minHits.data(), 4 * lut.minHits.size(), cudaMemcpyHostToDevice, stream));
@@ -854,7 +881,7 @@ void Ctx::upload_lut(int smaxNeeded)
   BANI_CUDA(cudaMemcpyAsync(d_ident.p, lut.ident.data(), 4 * lut.ident.size(), cudaMemcpyHostToDevice, stream));
   BANI_CUDA(cudaMemcpyAsync(d_upper.p, lut.upper.data(), 4 * lut.upper.size(), cudaMemcpyHostToDevice, stream));
   BANI_CUDA(cudaStreamSynchronize(stream));
-  lutUploaded = target;
+  lutUploaded = 1;
 }
 
 // ------------------------------------------------------------------ query sketch (stages A + B as an object)
@@ -1412,7 +1439,7 @@ void qsketch_map(Ctx *ctx, const Index *ix, const QSketch *const *sketches, int3
     if (wantCgi) { hCount.assign((size_t)nQc * nG, 0); hIdent.assign((size_t)nQc * nG, 0.f); }
 
     if (F > 0 && ix->M > 0) {
-      ctx->upload_lut(smax);
+      ctx->upload_lut(smax, pc.sCount.p, F);
 
       if (T > 0 && smax > 0) {
         // ---- C: lookup

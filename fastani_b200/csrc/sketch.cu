@@ -54,9 +54,19 @@ struct SketchArgs {
 
 // ------------------------------------------------------------------ MurmurHash3_x64_128, low 32 bits of h1
 __device__ __forceinline__ uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+// 64 x 64 -> low 64 bits with a constant: one wide multiply + two multiply-adds chained on the high word (3 instructions;
+// the compiler's own expansion spends a 4th on a separate add)
+__device__ __forceinline__ uint64_t mulc(uint64_t a, uint64_t c)
+{
+  const uint32_t alo = (uint32_t)a, ahi = (uint32_t)(a >> 32), clo = (uint32_t)c, chi = (uint32_t)(c >> 32);
+  uint32_t lo, hi;
+  asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %4;\n\tmov.b64 {%0, %1}, t;\n\tmad.lo.u32 %1, %2, %5, %1;\n\tmad.lo.u32 %1, %3, %4, %1;\n\t}"
+      : "=r"(lo), "=r"(hi) : "r"(alo), "r"(ahi), "r"(clo), "r"(chi));
+  return ((uint64_t)hi << 32) | lo;
+}
 __device__ __forceinline__ uint64_t fmix64(uint64_t k)
 {
-  k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33;
+  k ^= k >> 33; k = mulc(k, 0xff51afd7ed558ccdULL); k ^= k >> 33; k = mulc(k, 0xc4ceb9fe1a85ec53ULL); k ^= k >> 33;
   return k;
 }
 __device__ __forceinline__ uint64_t bytemask(int n) { return n >= 8 ? ~0ull : ((1ull << (8 * n)) - 1); }
@@ -71,23 +81,23 @@ __device__ __forceinline__ uint32_t murmur32(const uint64_t F[4], int krt)
   const int nblocks = k >> 4;
   if (nblocks >= 1) {
     uint64_t k1 = F[0], k2 = F[1];
-    k1 *= c1; k1 = rotl64(k1, 31); k1 *= c2; h1 ^= k1;
+    k1 = mulc(k1, c1); k1 = rotl64(k1, 31); k1 = mulc(k1, c2); h1 ^= k1;
     h1 = rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729;
-    k2 *= c2; k2 = rotl64(k2, 33); k2 *= c1; h2 ^= k2;
+    k2 = mulc(k2, c2); k2 = rotl64(k2, 33); k2 = mulc(k2, c1); h2 ^= k2;
     h2 = rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5;
   }
   if (nblocks == 2) {
     uint64_t k1 = F[2], k2 = F[3];
-    k1 *= c1; k1 = rotl64(k1, 31); k1 *= c2; h1 ^= k1;
+    k1 = mulc(k1, c1); k1 = rotl64(k1, 31); k1 = mulc(k1, c2); h1 ^= k1;
     h1 = rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729;
-    k2 *= c2; k2 = rotl64(k2, 33); k2 *= c1; h2 ^= k2;
+    k2 = mulc(k2, c2); k2 = rotl64(k2, 33); k2 = mulc(k2, c1); h2 ^= k2;
     h2 = rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5;
   }
   const int tail = k & 15;
   if (tail) {
     uint64_t t1 = nblocks ? F[2] : F[0], t2 = nblocks ? F[3] : F[1];
-    if (tail > 8) { uint64_t k2 = t2 & bytemask(tail - 8); k2 *= c2; k2 = rotl64(k2, 33); k2 *= c1; h2 ^= k2; }
-    uint64_t k1 = t1 & bytemask(tail < 8 ? tail : 8); k1 *= c1; k1 = rotl64(k1, 31); k1 *= c2; h1 ^= k1;
+    if (tail > 8) { uint64_t k2 = t2 & bytemask(tail - 8); k2 = mulc(k2, c2); k2 = rotl64(k2, 33); k2 = mulc(k2, c1); h2 ^= k2; }
+    uint64_t k1 = t1 & bytemask(tail < 8 ? tail : 8); k1 = mulc(k1, c1); k1 = rotl64(k1, 31); k1 = mulc(k1, c2); h1 ^= k1;
   }
   h1 ^= (uint64_t)k; h2 ^= (uint64_t)k;
   h1 += h2; h2 += h1;

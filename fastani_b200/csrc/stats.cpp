@@ -163,32 +163,65 @@ int stat_recommended_window_size(double p_value, int k, float identity, int frag
   return std::min(std::max(w, 1), fragLen);
 }
 
+static void lut_row(StatLut &L, int s, std::vector<long double> &scratch, int32_t &minHitsOut, std::vector<float> &idRow, std::vector<float> &ubRow)
+{
+  // estimateMinimumHitsRelaxed + the max(1, .) of computeL1CandidateRegions (computeMap.hpp:316-317)
+  int first = min_hits(s, L.k, L.pid);
+  int relaxed = first;
+  for (int i = first; i >= 0; i--) {
+    float jaccard = 1.0 * i / s;
+    float d = j2md(jaccard, L.k);
+    float d_lower = md_lower_bound(d, s, L.k, 0.9, scratch);
+    float id_upper = 100.0 * (1.0 - d_lower);
+    if (id_upper >= L.pid) relaxed = i; else break;
+  }
+  minHitsOut = relaxed < 1 ? 1 : relaxed;
+  idRow.resize(s + 1); ubRow.resize(s + 1);
+  for (int x = 0; x <= s; x++) identity_nolock(x, s, L.k, &idRow[x], &ubRow[x], scratch);
+}
+
 void StatLut::ensure(int s_needed)
 {
   if (s_needed <= smax) return;
   std::lock_guard<std::mutex> lk(g_mu);
   std::vector<long double> scratch;
-  if (minHits.empty()) { minHits.push_back(1); rowOff.push_back(0); ident.push_back(0.f); upper.push_back(0.f); }  // s = 0 row (unused)
+  if (minHits.empty()) { minHits.push_back(1); rowOff.push_back(0); ident.push_back(0.f); upper.push_back(0.f); have.push_back(1); }  // s = 0 row (unused)
+  if ((int)minHits.size() < s_needed + 1) { minHits.resize(s_needed + 1, 1); rowOff.resize(s_needed + 1, 0); have.resize(s_needed + 1, 0); }
+  std::vector<float> idRow, ubRow;
   for (int s = smax + 1; s <= s_needed; s++) {
-    // estimateMinimumHitsRelaxed + the max(1, .) of computeL1CandidateRegions (computeMap.hpp:316-317)
-    int first = min_hits(s, k, pid);
-    int relaxed = first;
-    for (int i = first; i >= 0; i--) {
-      float jaccard = 1.0 * i / s;
-      float d = j2md(jaccard, k);
-      float d_lower = md_lower_bound(d, s, k, 0.9, scratch);
-      float id_upper = 100.0 * (1.0 - d_lower);
-      if (id_upper >= pid) relaxed = i; else break;
-    }
-    minHits.push_back(relaxed < 1 ? 1 : relaxed);
-    rowOff.push_back((uint32_t)ident.size());
-    for (int x = 0; x <= s; x++) {
-      float id, ub;
-      identity_nolock(x, s, k, &id, &ub, scratch);
-      ident.push_back(id); upper.push_back(ub);
-    }
+    if (have[s]) continue;
+    int32_t mh;
+    lut_row(*this, s, scratch, mh, idRow, ubRow);
+    minHits[s] = mh;
+    rowOff[s] = (uint32_t)ident.size();
+    ident.insert(ident.end(), idRow.begin(), idRow.end()); upper.insert(upper.end(), ubRow.begin(), ubRow.end());
+    have[s] = 1;
   }
   smax = s_needed;
+}
+
+// Rows on demand: a row costs O(s^2) tail terms, so for very large sketches (tiny windows forced through the ABI) only
+// the sketch sizes that occur are computed instead of every s up to the maximum.
+bool StatLut::ensure_rows(const std::vector<int> &svals)
+{
+  std::lock_guard<std::mutex> lk(g_mu);
+  std::vector<long double> scratch;
+  if (minHits.empty()) { minHits.push_back(1); rowOff.push_back(0); ident.push_back(0.f); upper.push_back(0.f); have.push_back(1); }
+  bool added = false;
+  std::vector<float> idRow, ubRow;
+  for (int s : svals) {
+    if (s < 1) continue;
+    if ((int)minHits.size() < s + 1) { minHits.resize(s + 1, 1); rowOff.resize(s + 1, 0); have.resize(s + 1, 0); }
+    if (have[s]) continue;
+    int32_t mh;
+    lut_row(*this, s, scratch, mh, idRow, ubRow);
+    minHits[s] = mh;
+    rowOff[s] = (uint32_t)ident.size();
+    ident.insert(ident.end(), idRow.begin(), idRow.end()); upper.insert(upper.end(), ubRow.begin(), ubRow.end());
+    have[s] = 1;
+    added = true;
+  }
+  return added;
 }
 
 } // namespace bani

@@ -248,8 +248,8 @@ def test_hit_paths_agree():
     import subprocess, sys
     from conftest import ROOT
     outs = []
-    for cap, nb in (("8192", "4096"), ("0", "1024"), ("300", "4096"), ("1500", "1024")):   # all fast / all device-wide / two mixes; both L2 directory sizes
-        env = dict(os.environ, BANI_FRAG_L1_MAX=cap, BANI_L2E_BUCKETS=nb)
+    for cap, nb, stg in (("8192", "4096", "0"), ("0", "1024", "1"), ("300", "4096", "1"), ("1500", "1024", "0")):   # all fast / all device-wide / two mixes; both L2 directory sizes; direct / staged event stores
+        env = dict(os.environ, BANI_FRAG_L1_MAX=cap, BANI_L2E_BUCKETS=nb, BANI_L2_STAGE=stg)
         r = subprocess.run([sys.executable, "-c", _PATH_SCRIPT, ROOT], env=env, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stderr[-2000:]
         outs.append(r.stdout)
