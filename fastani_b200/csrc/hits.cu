@@ -129,26 +129,16 @@ frag_l1_kernel(const FragL1Args a, const uint32_t *list, uint32_t count)
   const unsigned long long base = a.hitOff[t0];
   const int n = (int)(a.hitOff[a.segStart[f + 1]] - base);
 
-  // ---- 1: gather.  Thread per OUTPUT slot: the owning position list is found by a binary search over the lists'
-  //         offsets (staged in shared memory), so all loads of a fragment are independent and neighbouring lanes read
-  //         neighbouring entries of the same few lists.  (Sketches larger than the staging area: thread per list.)
-  if (s <= 256) {
-    uint32_t *m_o = reinterpret_cast<uint32_t *>(hist), *m_lo = m_o + 260;
-    for (int q = tid; q < s; q += 256) { m_o[q] = (uint32_t)(a.hitOff[t0 + q] - base); m_lo[q] = a.hitLo[t0 + q]; }
-    if (tid == 0) m_o[s] = (uint32_t)n;
-    __syncthreads();
-    for (int i = tid; i < n; i += 256) {
-      int lo = 0, hi = s - 1;                     // last list whose offset is <= i
-      while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (m_o[mid] <= (uint32_t)i) lo = mid; else hi = mid - 1; }
-      bufA[i] = __ldg(&a.posIdx[m_lo[lo] + ((uint32_t)i - m_o[lo])]);
-    }
-    __syncthreads();
-  } else {
-    for (int q = tid; q < s; q += 256) {
-      const uint32_t lo = a.hitLo[t0 + q], cnt = a.hitCnt[t0 + q];
-      const uint32_t o = (uint32_t)(a.hitOff[t0 + q] - base);
-      for (uint32_t j = 0; j < cnt; j++) bufA[o + j] = __ldg(&a.posIdx[lo + j]);
-    }
+  // ---- 1: gather.  Lane per position list: a warp copies 32 lists side by side, element j of every list in step j (lists
+  //         are short -- one entry per related reference that holds the minimizer -- so a warp is done after max(count)
+  //         steps; the j-th and (j+1)-th element of a list share a sector, which stays in L1 between the steps)
+  for (int q = tid; q < ((s + 31) & ~31); q += 256) {
+    uint32_t lo = 0, cnt = 0, o = 0;
+    if (q < s) { lo = a.hitLo[t0 + q]; cnt = a.hitCnt[t0 + q]; o = (uint32_t)(a.hitOff[t0 + q] - base); }
+    uint32_t mx = cnt;
+#pragma unroll
+    for (int sh = 16; sh; sh >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, sh));
+    for (uint32_t j = 0; j < mx; j++) if (j < cnt) bufA[o + j] = __ldg(&a.posIdx[lo + j]);
   }
   for (int i = n + tid; i < CAP; i += 256) bufA[i] = 0xFFFFFFFFu;
   __syncthreads();
@@ -230,6 +220,82 @@ frag_l1_kernel(const FragL1Args a, const uint32_t *list, uint32_t count)
   if (tid == 0) a.candCount[f] = total;
 }
 
+// Fragments with few hits (shards of a multi-GPU run see a few hundred hits per fragment): one WARP per fragment instead
+// of a CTA -- no block barriers, a bitonic network on <= CAPW keys in a slice of shared memory instead of four radix
+// passes with their per-pass histogram work.  Same five steps, same outputs as frag_l1_kernel.
+template <int CAPW>
+__global__ void __launch_bounds__(128)
+frag_l1_warp_kernel(const FragL1Args a, const uint32_t *list, uint32_t count)
+{
+  __shared__ uint32_t sm[4][3 * CAPW];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint32_t slot = blockIdx.x * 4 + wid;
+  if (slot >= count) return;
+  const int f = (int)list[slot];
+  uint32_t *keys = sm[wid];
+  int32_t *s_w = reinterpret_cast<int32_t *>(keys + CAPW), *s_seq = s_w + CAPW;
+  const uint32_t t0 = a.segStart[f];
+  const int s = a.sCount[f];
+  const unsigned long long base = a.hitOff[t0];
+  const int n = (int)(a.hitOff[a.segStart[f + 1]] - base);
+  int n2 = 32; while (n2 < n) n2 <<= 1;
+  // ---- 1: gather, lane per position list (lists are short: about one hit per query hash here)
+  for (int q = lane; q < s; q += 32) {
+    const uint32_t cnt = a.hitCnt[t0 + q];
+    if (cnt) {
+      const uint32_t lo = a.hitLo[t0 + q], o = (uint32_t)(a.hitOff[t0 + q] - base);
+      for (uint32_t j = 0; j < cnt; j++) keys[o + j] = __ldg(&a.posIdx[lo + j]);
+    }
+  }
+  for (int i = n + lane; i < n2; i += 32) keys[i] = 0xFFFFFFFFu;
+  __syncwarp();
+  // ---- 2: sort by record index (bitonic, warp-synchronous)
+  for (int k2 = 2; k2 <= n2; k2 <<= 1)
+    for (int j = k2 >> 1; j > 0; j >>= 1) {
+      for (int t = lane; t < (n2 >> 1); t += 32) {
+        const int i = 2 * t - (t & (j - 1)), p = i + j;
+        const uint32_t x = keys[i], y = keys[p];
+        const bool asc = (i & k2) == 0;
+        if ((x > y) == asc) { keys[i] = y; keys[p] = x; }
+      }
+      __syncwarp();
+    }
+  // ---- 3: (wpos, seqId) of the sorted hits
+  for (int r = lane; r < n; r += 32) { const int2 p = __ldg(&a.recPos[keys[r]]); s_w[r] = p.x; s_seq[r] = p.y; }
+  __syncwarp();
+  // ---- 4 + 5: region rule on 32 consecutive ranks at a time; a ballot of the raw-region flags of the NEXT 32 ranks is
+  //             needed for the right neighbour of lane 31, so the flags of every block are computed one block ahead
+  const int mh = a.minHits[s];
+  auto qual = [&](int r) -> bool {
+    const int rb = r + mh - 1;
+    return r < n && rb < n && s_seq[rb] == s_seq[r] && s_w[rb] - s_w[r] < a.fragLen;
+  };
+  auto start_of = [&](int r) -> int32_t { return max(0, s_w[r + mh - 1] - a.fragLen + 1); };
+  uint32_t run = 0;
+  uint32_t qPrev = 0, qCur = __ballot_sync(0xffffffffu, qual(lane));
+  for (int r0 = 0; r0 < n; r0 += 32) {
+    const uint32_t qNext = __ballot_sync(0xffffffffu, qual(r0 + 32 + lane));
+    const int r = r0 + lane;
+    bool hd = false, tl = false;
+    int32_t st = 0;
+    if ((qCur >> lane) & 1u) {
+      st = start_of(r);
+      const bool qL = lane ? ((qCur >> (lane - 1)) & 1u) : ((qPrev >> 31) & 1u);
+      const bool qR = lane < 31 ? ((qCur >> (lane + 1)) & 1u) : (qNext & 1u);
+      const bool merged = r > 0 && qL && s_seq[r - 1] == s_seq[r] && s_w[r - 1] >= st;
+      const bool nextMerges = r + 1 < n && qR && s_seq[r + 1] == s_seq[r] && s_w[r] >= start_of(r + 1);
+      hd = !merged; tl = !nextMerges;
+    }
+    const uint32_t hb = __ballot_sync(0xffffffffu, hd);
+    const uint32_t upto = run + __popc(hb & ((2u << lane) - 1u));           // heads at ranks <= mine
+    if (hd) { a.stSeq[base + upto - 1] = s_seq[r]; a.stStart[base + upto - 1] = st; }
+    if (tl) a.stEnd[base + upto - 1] = s_w[r];
+    run += __popc(hb);
+    qPrev = qCur; qCur = qNext;
+  }
+  if (lane == 0) a.candCount[f] = run;
+}
+
 template <int ITEMS>
 static void launch_class(Ctx *ctx, const FragL1Args &a, const uint32_t *list, uint32_t count, cudaStream_t st)
 {
@@ -256,8 +322,9 @@ void frag_l1_fast(Ctx *ctx, const FragL1Args &a, const uint32_t *classList, cons
   const size_t F = (size_t)a.F;
   // one instantiation per size class (frag_class_items): the sort works on 256 * ITEMS slots, so narrow classes
   // keep the padding of a fragment's hit list small
-  launch_class<1>(ctx, a, classList + 0 * F, classCount[0], st);
-  launch_class<2>(ctx, a, classList + 1 * F, classCount[1], st);
+  // up to 512 hits: warp per fragment
+  if (classCount[0]) frag_l1_warp_kernel<256><<<(classCount[0] + 3) / 4, 128, 0, st>>>(a, classList + 0 * F, classCount[0]);
+  if (classCount[1]) frag_l1_warp_kernel<512><<<(classCount[1] + 3) / 4, 128, 0, st>>>(a, classList + 1 * F, classCount[1]);
   launch_class<3>(ctx, a, classList + 2 * F, classCount[2], st);
   launch_class<4>(ctx, a, classList + 3 * F, classCount[3], st);
   launch_class<5>(ctx, a, classList + 4 * F, classCount[4], st);

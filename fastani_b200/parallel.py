@@ -45,10 +45,10 @@ def merge_shards(tables, n_queries, n_refs, world):
     tot = None
     for g, t in enumerate(tables):
         c, i = t[0], t[1]
-        cols = shard_refs(n_refs, world, g)
-        if cols:
-            cnt[:, cols] = c[:, :len(cols)]
-            idn[:, cols] = i[:, :len(cols)]
+        ncols = len(range(g, n_refs, world))                 # shard g owns the columns g, g + world, ... (shard_refs)
+        if ncols:
+            cnt[:, g::world] = c[:, :ncols]
+            idn[:, g::world] = i[:, :ncols]
         if len(t) > 2 and t[2] is not None:
             tot = t[2].copy() if tot is None else np.maximum(tot, t[2])
     return (cnt, idn) if tot is None else (cnt, idn, tot)
