@@ -200,7 +200,7 @@ class Context:
 
     def profile_read(self):
         """{stage: (ms, algorithmic_bytes, launches)} accumulated since the last read."""
-        nmax = 64
+        nmax = 128
         names = (C.c_char * 32 * nmax)()
         ms = (C.c_double * nmax)(); by = (C.c_double * nmax)(); la = (C.c_int32 * nmax)(); n = C.c_int32()
         _check(self.lib.bani_ctx_profile_read(self.h, names, ms, by, la, nmax, C.byref(n)))

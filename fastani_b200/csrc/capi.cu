@@ -167,18 +167,31 @@ int bani_ctx_profile_read(bani_ctx *ctx, char (*names)[32], double *ms, double *
   BANI_CUDA(cudaSetDevice(ctx->c.device));
   BANI_CUDA(cudaStreamSynchronize(ctx->c.stream));
   int cnt = 0;
-  for (auto &e : ctx->c.profEvents) {
-    float t = 0; cudaEventElapsedTime(&t, e.a, e.b);
-    cudaEventDestroy(e.a); cudaEventDestroy(e.b);
+  auto add = [&](const char *name, float t, double bytes) {
     int j = 0;
-    for (; j < cnt; j++) if (strncmp(names[j], e.name, 31) == 0) break;
+    for (; j < cnt; j++) if (strncmp(names[j], name, 31) == 0) break;
     if (j == cnt) {
-      if (cnt >= n_max) continue;
-      strncpy(names[j], e.name, 31); names[j][31] = 0; ms[j] = 0; algo_bytes[j] = 0; launches[j] = 0; cnt++;
+      if (cnt >= n_max) return;
+      strncpy(names[j], name, 31); names[j][31] = 0; ms[j] = 0; algo_bytes[j] = 0; launches[j] = 0; cnt++;
     }
-    ms[j] += t; algo_bytes[j] += e.bytes; launches[j] += 1;
+    ms[j] += t; algo_bytes[j] += bytes; launches[j] += 1;
+  };
+  auto &evs = ctx->c.profEvents;
+  for (size_t i = 0; i < evs.size(); i++) {
+    float t = 0; cudaEventElapsedTime(&t, evs[i].a, evs[i].b);
+    add(evs[i].name, t, evs[i].bytes);
+    // device time between the end of the previous stage and the start of this one (kernels outside the stage timers,
+    // memsets / copies, and idle time while the host decides what to launch next), filed under "gap>stage"
+    if (i > 0) {
+      float g = 0;
+      if (cudaEventElapsedTime(&g, evs[i - 1].b, evs[i].a) == cudaSuccess && g > 0) {
+        char nm[32]; snprintf(nm, sizeof nm, "gap>%s", evs[i].name);
+        add(nm, g, 0.0);
+      } else (void)cudaGetLastError();
+    }
   }
-  ctx->c.profEvents.clear();
+  for (auto &e : evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+  evs.clear();
   *n = cnt;
   return BANI_OK;
   BANI_CATCH

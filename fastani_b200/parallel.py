@@ -1,9 +1,10 @@
-"""Multi-GPU layout of a many-to-many run: one process per GPU, references sharded round-robin.
+"""Multi-GPU layout of a many-to-many run: one process per GPU, the reference list cut into one shard per GPU.
 
-This is exactly the reference's threading rule lifted to GPUs (src/cgi/include/
-computeCoreIdentity.hpp:457-487): shard g owns references j with j % G == g, every shard maps
-ALL queries against its own index, results of different shards are disjoint, and a local
-reference id becomes global as local * G + g.  Two exchanges: (1) the query sketches -- rank r sketches the
+This is the reference's threading rule lifted to GPUs (src/cgi/include/computeCoreIdentity.hpp:457-487): every shard
+maps ALL queries against its own index, results of different shards are disjoint, and a local reference id becomes
+global again afterwards.  The reference deals references round-robin (shard g owns j with j % G == g, global id =
+local * G + g: partition "interleave"); contiguous blocks of the list (partition "block") give the same results and keep
+list neighbours on one GPU.  Two exchanges: (1) the query sketches -- rank r sketches the
 queries r, r+G, ... once and the sorted fragment sketches (~0.33 B per query base) are all-gathered over NCCL,
 so the query-side work is not repeated on every rank; (2) the final gather of the dense per-pair tables
 (count int32, identity float32).
@@ -11,13 +12,24 @@ so the query-side work is not repeated on every rank; (2) the final gather of th
 import numpy as np
 
 
-def shard_refs(n_refs, world, rank):
-    """splitReferenceGenomes (computeCoreIdentity.hpp:457-474): indices of the references of shard `rank`."""
+def shard_refs(n_refs, world, rank, partition="interleave"):
+    """Indices of the references of shard `rank`.
+    "interleave": splitReferenceGenomes (computeCoreIdentity.hpp:457-474), reference j -> shard j % world.
+    "block": contiguous ranges of the list.  Per-pair results do not depend on the partition (the
+    shard-invariance tests), so a run is free to choose: a block partition keeps genomes that are neighbours in the list
+    on one GPU -- lists ordered by taxon, as directory listings usually are, then leave each query fragment with
+    candidates in ONE shard instead of a few in every shard -- while interleaving balances the load for any order."""
+    if partition == "block":
+        a = (n_refs * rank) // world
+        b = (n_refs * (rank + 1)) // world
+        return list(range(a, b))
     return list(range(rank, n_refs, world))
 
 
-def global_ref_id(local_id, world, rank):
-    """correctRefGenomeIds (computeCoreIdentity.hpp:480-487)."""
+def global_ref_id(local_id, world, rank, n_refs=None, partition="interleave"):
+    """correctRefGenomeIds (computeCoreIdentity.hpp:480-487); for a block partition: offset of the block."""
+    if partition == "block":
+        return (n_refs * rank) // world + local_id
     return local_id * world + rank
 
 
@@ -37,7 +49,7 @@ def dense_tables(cgi_results, n_queries, n_local_refs, total_fragments=None):
     return cnt, idn, tot
 
 
-def merge_shards(tables, n_queries, n_refs, world):
+def merge_shards(tables, n_queries, n_refs, world, partition="interleave"):
     """tables[g] = (count, identity[, totals]) of shard g, shapes [n_queries, len(shard_refs(n_refs, world, g))].
     Returns the global [n_queries, n_refs] tables (and the element-wise maximum of the totals when present)."""
     cnt = np.zeros((n_queries, n_refs), np.int32)
@@ -45,22 +57,68 @@ def merge_shards(tables, n_queries, n_refs, world):
     tot = None
     for g, t in enumerate(tables):
         c, i = t[0], t[1]
-        ncols = len(range(g, n_refs, world))                 # shard g owns the columns g, g + world, ... (shard_refs)
-        if ncols:
-            cnt[:, g::world] = c[:, :ncols]
-            idn[:, g::world] = i[:, :ncols]
+        if partition == "block":
+            a, b = (n_refs * g) // world, (n_refs * (g + 1)) // world
+            if b > a:
+                cnt[:, a:b] = c[:, :b - a]
+                idn[:, a:b] = i[:, :b - a]
+        else:
+            ncols = len(range(g, n_refs, world))             # shard g owns the columns g, g + world, ... (shard_refs)
+            if ncols:
+                cnt[:, g::world] = c[:, :ncols]
+                idn[:, g::world] = i[:, :ncols]
         if len(t) > 2 and t[2] is not None:
             tot = t[2].copy() if tot is None else np.maximum(tot, t[2])
     return (cnt, idn) if tot is None else (cnt, idn, tot)
 
 
-def gather_tables(cnt_local, idn_local, n_refs, world, rank, dist=None, device=None, tot=None):
+def gather_rows(cgi_results, n_queries, n_refs, world, rank, dist=None, device=None, total_fragments=None, partition="interleave"):
+    """The result exchange of a multi-GPU run on the COMPACT rows: every rank contributes its cgi::CGI_Results rows
+    (20 bytes each; a few thousand per rank instead of a dense n_queries x n_refs / world table), one padded all-gather,
+    reference ids made global (correctRefGenomeIds), dense tables filled once.  Returns (count, identity, totals)."""
+    rows = np.ascontiguousarray(cgi_results)
+    cnt = np.zeros((n_queries, n_refs), np.int32)
+    idn = np.zeros((n_queries, n_refs), np.float32)
+    tot = np.zeros(n_queries, np.int32)
+    if total_fragments is not None:
+        tot[:len(total_fragments)] = np.asarray(total_fragments, np.int64).astype(np.int32)
+
+    def fill(r, g):
+        if len(r):
+            ref = global_ref_id(r["refGenomeId"].astype(np.int64), world, g, n_refs, partition)
+            cnt[r["qryGenomeId"], ref] = r["countSeq"]
+            idn[r["qryGenomeId"], ref] = r["identity"]
+            tot[r["qryGenomeId"]] = np.maximum(tot[r["qryGenomeId"]], r["totalQueryFragments"])
+
+    if world == 1 or dist is None:
+        fill(rows, 0)
+        return cnt, idn, tot
+    import torch
+    n = torch.tensor([len(rows)], dtype=torch.int64, device=device if device is not None else "cpu")
+    ns = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(ns, n)
+    ns = [int(x.item()) for x in ns]
+    width = max(max(ns), 1)
+    buf = np.zeros((width, rows.dtype.itemsize // 4), np.int32)
+    buf[:len(rows)] = rows.view(np.int32).reshape(len(rows), -1)
+    t = torch.from_numpy(buf)
+    if device is not None:
+        t = t.to(device)
+    out = torch.empty((world * width, buf.shape[1]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, t)
+    o = out.cpu().numpy().reshape(world, width, buf.shape[1])
+    for g in range(world):
+        fill(np.ascontiguousarray(o[g, :ns[g]]).view(rows.dtype).reshape(-1), g)
+    return cnt, idn, tot
+
+
+def gather_tables(cnt_local, idn_local, n_refs, world, rank, dist=None, device=None, tot=None, partition="interleave"):
     """All-gather of the per-shard tables over torch.distributed (NCCL on GPUs, gloo on CPU): shards are padded to the
     largest shard and count / identity bits / totals travel as ONE int32 tensor in one collective.
     Returns (count, identity) or, when `tot` is given, (count, identity, totals)."""
     n_queries = cnt_local.shape[0]
     if world == 1 or dist is None:
-        return merge_shards([(cnt_local, idn_local, tot)], n_queries, n_refs, 1)
+        return merge_shards([(cnt_local, idn_local, tot)], n_queries, n_refs, 1, partition)
     import torch
     width = (n_refs + world - 1) // world
     pack = np.zeros((n_queries, 2 * width + 1), np.int32)
@@ -75,7 +133,7 @@ def gather_tables(cnt_local, idn_local, n_refs, world, rank, dist=None, device=N
     dist.all_gather_into_tensor(out, t)
     o = out.cpu().numpy().reshape(world, t.shape[0], t.shape[1])
     tables = [(o[g][:, :width], o[g][:, width:2 * width].view(np.float32), o[g][:, 2 * width] if tot is not None else None) for g in range(world)]
-    return merge_shards(tables, n_queries, n_refs, world)
+    return merge_shards(tables, n_queries, n_refs, world, partition)
 
 
 class SketchExchange:

@@ -43,6 +43,18 @@ c, i, t = run(mine)
 gc, gi, gt = parallel.gather_tables(c, i, len(genomes), world, rank, dist=dist, tot=t)
 gc2, gi2 = parallel.gather_tables(c, i, len(genomes), world, rank, dist=dist)
 assert (gc2 == gc).all() and (gi2.view(np.uint32) == gi.view(np.uint32)).all()
+# the compact-row exchange, for the reference's round-robin deal and for contiguous blocks
+from fastani_b200.api import CGI_DTYPE
+fc0, fi0, ft0 = run(list(range(len(genomes))))
+for part in ("interleave", "block"):
+    ids = parallel.shard_refs(len(genomes), world, rank, part)
+    lc, li, lt = run(ids)
+    qq, rr = np.nonzero(lc)
+    rows = np.zeros(len(qq), CGI_DTYPE)
+    rows["qryGenomeId"], rows["refGenomeId"], rows["countSeq"], rows["identity"], rows["totalQueryFragments"] = qq, rr, lc[qq, rr], li[qq, rr], lt[qq]
+    rc, ri, rt = parallel.gather_rows(rows, len(queries), len(genomes), world, rank, dist=dist, partition=part)
+    assert (rc == fc0).all() and (ri.view(np.uint32) == fi0.view(np.uint32)).all() and (rt == ft0).all(), part
+    assert [parallel.global_ref_id(i, world, rank, len(genomes), part) for i in range(len(ids))] == ids
 if rank == 0:
     fc, fi, ft = run(list(range(len(genomes))))
     assert (gt == ft).all() and (ft == L // 3000).all(), (gt, ft)

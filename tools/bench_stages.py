@@ -33,4 +33,4 @@ for it in range(reps):
     sk.close()
 print("step %.1f ms (index %.1f + map %.1f)  pairs/s %.0f  counters %s" % (dt * 1e3, (t1 - t) * 1e3, (dt - (t1 - t)) * 1e3, nG * nG / dt, ctr.as_dict()))
 for k, v in prof.items():
-    print("  %-16s %9.2f ms  x%d" % (k, v[0], v[2]))
+    print("  %-22s %9.2f ms  x%d" % (k, v[0], v[2]))

@@ -7,8 +7,8 @@ fragments, mappings).  COUNTERS.json holds the integer counters of the captured 
 prints, plus "bases").  Run where ncu is installed."""
 import csv, io, json, re, subprocess, sys
 
-GROUP_OF = [(r"(?<![a-z_])sketch_kernel", "hp1_index_build", "bases"), (r"lookup_kernel", "hp2_lookup", "probes"),
-            (r"frag_l1_kernel|frag_classify|cand_compact", "hp2_hits_l1", "hits"),
+GROUP_OF = [(r"(?<![a-z_])sketch_kernel|zip_records|table_fill|links_kernel|head_flags|unique_scatter|block_link_max|dir_fill", "hp1_index_build", "bases"), (r"lookup_kernel", "hp2_lookup", "probes"),
+            (r"frag_l1_kernel|frag_l1_warp_kernel|frag_classify|cand_compact", "hp2_hits_l1", "hits"),
             (r"l2_bounds_kernel|l2_events_kernel|l2_seq_kernel|l2_kernel", "hp2_l2", "records"),
             (r"sort_unique|frag_ref_|compact_sketch", "hp2_query_sketch", "fragments"), (r"rows_kernel|cgi_", "hp2_report_cgi", "mappings")]
 
