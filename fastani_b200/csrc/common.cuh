@@ -170,6 +170,10 @@ struct Index {
   // bucket = LOW bits of the hash (uniform, unlike the top bits of a minimizer hash); x == 0 = empty.  A full bucket or a
   // saturated count sends the probe to the sorted keys above (index.cu: table_fill_kernel, map.cu: lookup_kernel)
   DevBuf<uint2> tab; int tabBits = 0;
+  // membership filter in front of the probe table for small shards (multi-GPU): one bit per value of the low filtBits bits
+  // of the hash, sized 8x the unique hashes and at most 64 MB so that it stays L2-resident; a clear bit answers a miss
+  // without touching DRAM (most probes of a shard are misses when the queries of other shards are mapped against it)
+  DevBuf<uint32_t> filt; int filtBits = 0;
   std::vector<int32_t> contigLen;    // host copies
   std::vector<int32_t> seqsByFile;   // cumulative contig count per genome (sequencesByFileInfo)
   // Which genomes the index was built from (uid -> first contig ordinal) and, per hashed position, whether it was

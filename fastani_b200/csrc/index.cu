@@ -141,11 +141,13 @@ __global__ void dir_fill_kernel(const uint32_t *ukeys, uint32_t U, int dirBits, 
 // Probe table of the lookup stage (Index::tab): every unique hash claims one of the 4 slots of bucket (hash & mask) with
 // a 64-bit compare-and-swap; keys that find their bucket full stay reachable through the sorted key array.  Which 4 keys
 // of an overfull bucket get in depends on the order of the atomics, the result of a lookup does not.
-__global__ void table_fill_kernel(const uint32_t *ukeys, const uint32_t *uoff, uint32_t U, uint32_t mask, uint2 *tab)
+__global__ void table_fill_kernel(const uint32_t *ukeys, const uint32_t *uoff, uint32_t U, uint32_t mask, uint2 *tab,
+                                  uint32_t *filt, uint32_t filtMask)
 {
   const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
   if (u >= U) return;
   const uint32_t h = ukeys[u], o = uoff[u], cnt = uoff[u + 1] - o;
+  if (filt) atomicOr(&filt[(h & filtMask) >> 5], 1u << (h & 31u));
   const unsigned long long e = ((unsigned long long)o << 32) | (unsigned long long)((h & 0xFFFFFF00u) | min(cnt, 255u));
   unsigned long long *bp = reinterpret_cast<unsigned long long *>(tab + 4 * (size_t)(h & mask));
 #pragma unroll
@@ -259,7 +261,12 @@ static void index_finish(Ctx *ctx, Index *ix)
     ix->tabBits = tb;
     ix->tab.alloc((size_t)4 << tb, st);
     BANI_CUDA(cudaMemsetAsync(ix->tab.p, 0, ix->tab.bytes(), st));
-    table_fill_kernel<<<nblk(U), 256, 0, st>>>(ix->ukeys.p, ix->uoff.p, (uint32_t)U, (1u << tb) - 1u, ix->tab.p);
+    int fb = 0;
+    if (U <= (1ull << 26)) { fb = 8; while ((1ull << fb) < U) fb++; fb = std::min(fb + 3, 29); }      // <= 64 MB of bits
+    ix->filtBits = fb;
+    if (fb) { ix->filt.alloc((size_t)1 << (fb - 5), st); BANI_CUDA(cudaMemsetAsync(ix->filt.p, 0, ix->filt.bytes(), st)); }
+    table_fill_kernel<<<nblk(U), 256, 0, st>>>(ix->ukeys.p, ix->uoff.p, (uint32_t)U, (1u << tb) - 1u, ix->tab.p,
+                                               ix->filt.p, fb ? (uint32_t)((1ull << fb) - 1ull) : 0u);
     ctx->launches++;
   }
   ix->rec.alloc(M, st);

@@ -141,12 +141,14 @@ __device__ __forceinline__ int seg_of(const uint32_t *segStart, int F, uint32_t 
 // saturated count, walks the sorted keys (bucket directory over the top bits, then a short binary search).
 __global__ void lookup_kernel(const uint32_t *fragHash, uint32_t T, const uint2 *tab, uint32_t tabMask,
                               const uint32_t *ukeys, const uint32_t *uoff, const uint32_t *dir, int dirBits,
-                              uint32_t *hitLo, uint32_t *hitCnt)
+                              const uint32_t *filt, uint32_t filtMask, uint32_t *hitLo, uint32_t *hitCnt)
 {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t > T) return;
   if (t == T) { hitCnt[t] = 0; hitLo[t] = 0; return; }
   const uint32_t h = __ldg(&fragHash[t]);
+  // small shards: an L2-resident membership bit decides most misses without a DRAM access
+  if (filt && !((__ldg(&filt[(h & filtMask) >> 5]) >> (h & 31u)) & 1u)) { hitLo[t] = 0; hitCnt[t] = 0; return; }
   const uint4 *bp = reinterpret_cast<const uint4 *>(tab) + 2 * (size_t)(h & tabMask);
   const uint4 e0 = __ldg(bp), e1 = __ldg(bp + 1);
   const uint32_t key = h & 0xFFFFFF00u;
@@ -1448,7 +1450,8 @@ void qsketch_map(Ctx *ctx, const Index *ix, const QSketch *const *sketches, int3
         BANI_SCRATCH(unsigned long long, hitOff, T + 1);
         { Stage sg(ctx, "lookup", 12.0 * T);
           lookup_kernel<<<nblk(T + 1), 256, 0, st>>>(fragHash.p, (uint32_t)T, ix->tab.p, (1u << ix->tabBits) - 1u, ix->ukeys.p, ix->uoff.p,
-                                                   ix->dir.p, ix->dirBits, hitLo.p, hitCnt.p);
+                                                   ix->dir.p, ix->dirBits, ix->filt.p, ix->filtBits ? (uint32_t)((1ull << ix->filtBits) - 1ull) : 0u,
+                                                   hitLo.p, hitCnt.p);
           ctx->launches++;
           size_t tb = cub_scan_u64_temp(T + 1);
           BANI_SCRATCH(uint8_t, tmp, tb);

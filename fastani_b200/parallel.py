@@ -72,32 +72,40 @@ def merge_shards(tables, n_queries, n_refs, world, partition="interleave"):
     return (cnt, idn) if tot is None else (cnt, idn, tot)
 
 
-def gather_rows(cgi_results, n_queries, n_refs, world, rank, dist=None, device=None, total_fragments=None, partition="interleave"):
+def gather_rows(cgi_results, n_queries, n_refs, world, rank, dist=None, device=None, total_fragments=None, partition="interleave", out=None):
     """The result exchange of a multi-GPU run on the COMPACT rows: every rank contributes its cgi::CGI_Results rows
     (20 bytes each; a few thousand per rank instead of a dense n_queries x n_refs / world table), one padded all-gather,
     reference ids made global (correctRefGenomeIds), dense tables filled once.  Returns (count, identity, totals)."""
     rows = np.ascontiguousarray(cgi_results)
-    cnt = np.zeros((n_queries, n_refs), np.int32)
-    idn = np.zeros((n_queries, n_refs), np.float32)
-    tot = np.zeros(n_queries, np.int32)
+    if out is not None:                                      # reuse the caller's tables (no fresh 8 MB of pages per step)
+        cnt, idn, tot = out
+        cnt.fill(0); idn.fill(0); tot.fill(0)
+    else:
+        cnt = np.zeros((n_queries, n_refs), np.int32)
+        idn = np.zeros((n_queries, n_refs), np.float32)
+        tot = np.zeros(n_queries, np.int32)
     if total_fragments is not None:
         tot[:len(total_fragments)] = np.asarray(total_fragments, np.int64).astype(np.int32)
 
+    cflat, iflat = cnt.reshape(-1), idn.reshape(-1)
+
     def fill(r, g):
         if len(r):
-            ref = global_ref_id(r["refGenomeId"].astype(np.int64), world, g, n_refs, partition)
-            cnt[r["qryGenomeId"], ref] = r["countSeq"]
-            idn[r["qryGenomeId"], ref] = r["identity"]
-            tot[r["qryGenomeId"]] = np.maximum(tot[r["qryGenomeId"]], r["totalQueryFragments"])
+            w = r.view(np.int32).reshape(len(r), -1)             # columns: refGenomeId qryGenomeId countSeq totalQueryFragments identity-bits
+            q = w[:, 1].astype(np.int64)
+            flat = q * n_refs + global_ref_id(w[:, 0].astype(np.int64), world, g, n_refs, partition)
+            cflat[flat] = w[:, 2]
+            iflat[flat] = w[:, 4].view(np.float32)
+            np.maximum.at(tot, q, w[:, 3])
 
     if world == 1 or dist is None:
         fill(rows, 0)
         return cnt, idn, tot
     import torch
     n = torch.tensor([len(rows)], dtype=torch.int64, device=device if device is not None else "cpu")
-    ns = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(ns, n)
-    ns = [int(x.item()) for x in ns]
+    nall = torch.empty(world, dtype=torch.int64, device=n.device)
+    dist.all_gather_into_tensor(nall, n)
+    ns = [int(x) for x in nall.cpu()]
     width = max(max(ns), 1)
     buf = np.zeros((width, rows.dtype.itemsize // 4), np.int32)
     buf[:len(rows)] = rows.view(np.int32).reshape(len(rows), -1)
