@@ -46,6 +46,7 @@ struct Parameters {                                       // map_parameters.hpp:
   float maxRatioDiff = 100.0f;
   bool sanityCheck = false;
   int gpus = 0;                                           // extension: devices to shard the references over (0 = all visible)
+  bool blockPartition = false;                            // extension: --partition block (contiguous reference shards instead of the round-robin deal)
   std::string saveIndex, loadIndex;                       // extension: on-disk sketch cache (prefix of <prefix>.meta + <prefix>.<g>of<N>.idx)
   bani_params c() const
   {
@@ -297,14 +298,20 @@ inline void computeCGI(const skch::Parameters &parameters, const skch::MappingRe
 }
 
 // computeCoreIdentity.hpp:457-474: reference j goes to shard j % G
-inline std::vector<std::vector<int>> splitReferenceGenomes(int nRefs, int G)
+// (block = true: contiguous ranges of the list instead -- same results, list neighbours stay on one GPU)
+inline std::vector<std::vector<int>> splitReferenceGenomes(int nRefs, int G, bool block = false)
 {
   std::vector<std::vector<int>> s(G);
-  for (int j = 0; j < nRefs; j++) s[j % G].push_back(j);
+  if (block) { for (int g = 0; g < G; g++) for (int j = (int)((int64_t)nRefs * g / G); j < (int)((int64_t)nRefs * (g + 1) / G); j++) s[g].push_back(j); }
+  else for (int j = 0; j < nRefs; j++) s[j % G].push_back(j);
   return s;
 }
 // computeCoreIdentity.hpp:480-487: shard-local reference id -> global id
-inline void correctRefGenomeIds(std::vector<CGI_Results> &v, int shard, int G) { for (auto &e : v) e.refGenomeId = e.refGenomeId * G + shard; }
+inline void correctRefGenomeIds(std::vector<CGI_Results> &v, int shard, int G, int nRefs = 0, bool block = false)
+{
+  const int base = block ? (int)((int64_t)nRefs * shard / G) : 0;
+  for (auto &e : v) e.refGenomeId = block ? base + e.refGenomeId : e.refGenomeId * G + shard;
+}
 
 inline bool passesMinFraction(const skch::Parameters &p, const CGI_Results &e, uint64_t qLen, uint64_t rLen)
 {

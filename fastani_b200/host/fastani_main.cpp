@@ -46,6 +46,8 @@ static void usage(const char *prog, std::ostream &o)
        "     --minFraction <value> minimum fraction of genome that must be shared for trusting ANI [default : 0.2]\n"
        "     --maxRatioDiff <value> maximum difference between (Total Ref. Length/Total Occ. Hashes) and\n"
        "                           (Total Ref. Length/Total No. Hashes) [default : 100.0]\n"
+       "     --partition <value>   how the reference list is cut into one shard per GPU: interleave (the reference's round-robin\n"
+       "                           deal, default) or block (contiguous ranges: list neighbours stay on one GPU)\n"
        "     --saveIndex <prefix>  write the reference sketches to <prefix>.meta + <prefix>.<shard>of<N>.idx after building them\n"
        "     --loadIndex <prefix>  take the references from a saved index instead of -r/--rl: no reference file is read or\n"
        "                           sketched again; queries that are genomes of the index need no file either (1 GPU)\n"
@@ -97,6 +99,7 @@ static void parseandSave(int argc, char **argv, Parameters &p)
     else if (a == "--fragLen") p.minReadLength = atoi(need(i));
     else if (a == "--minFraction") p.minFraction = (float)atof(need(i));
     else if (a == "--maxRatioDiff") p.maxRatioDiff = (float)atof(need(i));
+    else if (a == "--partition") { const std::string v = need(i); if (v == "block") p.blockPartition = true; else if (v != "interleave") { usage(argv[0], std::cout); exit(1); } }
     else if (a == "--saveIndex") p.saveIndex = need(i);
     else if (a == "--loadIndex") p.loadIndex = need(i);
     else if (a == "--visualize") p.visualize = true;
@@ -133,6 +136,7 @@ static void parseandSave(int argc, char **argv, Parameters &p)
 //      contig names -- plus the parameters, so that a mismatch is reported before any GPU work
 struct IndexMeta {
   int k = 0, fragLen = 0, window = 0, shards = 0;
+  bool block = false;                                                 // version 2: the shards are contiguous blocks of the list
   std::vector<std::string> refPaths;                                  // global reference order
   std::vector<std::vector<std::string>> contigNames;                  // per shard, seqId order
 };
@@ -142,7 +146,7 @@ static void writeMeta(const std::string &prefix, const Parameters &p, int G, con
 {
   std::ofstream o(prefix + ".meta");
   if (!o) throw std::runtime_error("cannot write " + prefix + ".meta");
-  o << "BANI_INDEX_META\t1\n" << p.kmerSize << "\t" << p.minReadLength << "\t" << p.windowSize << "\t" << G << "\t" << p.refSequences.size() << "\n";
+  o << "BANI_INDEX_META\t" << (p.blockPartition ? 2 : 1) << "\n" << p.kmerSize << "\t" << p.minReadLength << "\t" << p.windowSize << "\t" << G << "\t" << p.refSequences.size() << "\n";
   for (const auto &r : p.refSequences) o << r << "\n";
   for (int g = 0; g < G; g++) { o << contigNames[g].size() << "\n"; for (const auto &n : contigNames[g]) o << n << "\n"; }
 }
@@ -153,7 +157,8 @@ static IndexMeta readMeta(const std::string &prefix)
   if (!in) throw std::runtime_error("cannot open " + prefix + ".meta");
   IndexMeta m; std::string tag; int ver = 0; size_t nRefs = 0;
   in >> tag >> ver >> m.k >> m.fragLen >> m.window >> m.shards >> nRefs;
-  if (!in || tag != "BANI_INDEX_META" || ver != 1 || m.shards < 1) throw std::runtime_error(prefix + ".meta is not an index metadata file");
+  if (!in || tag != "BANI_INDEX_META" || (ver != 1 && ver != 2) || m.shards < 1) throw std::runtime_error(prefix + ".meta is not an index metadata file");
+  m.block = ver == 2;
   std::string line; std::getline(in, line);
   for (size_t i = 0; i < nRefs; i++) { if (!std::getline(in, line)) throw std::runtime_error(prefix + ".meta is truncated"); m.refPaths.push_back(line); }
   m.contigNames.resize(m.shards);
@@ -201,6 +206,7 @@ int main(int argc, char **argv)
         throw std::runtime_error("the saved index was built with k " + std::to_string(meta.k) + " fragLen " + std::to_string(meta.fragLen) + " window " + std::to_string(meta.window) +
                                  ", this run asks for k " + std::to_string(parameters.kmerSize) + " fragLen " + std::to_string(parameters.minReadLength) + " window " + std::to_string(parameters.windowSize));
       parameters.refSequences = meta.refPaths;
+      parameters.blockPartition = meta.block;
     }
     // a run that names its GPU count initialises only those devices (the driver's start-up cost grows with every visible GPU)
     {
@@ -214,7 +220,7 @@ int main(int argc, char **argv)
     if (bani_device_count(&nDev) != BANI_OK || nDev == 0) throw std::runtime_error("no CUDA device available (this program has no CPU path)");
     const int G = loading ? meta.shards : (parameters.gpus > 0 ? std::min(parameters.gpus, nDev) : nDev);
     if (G > nDev) throw std::runtime_error("the saved index has " + std::to_string(G) + " shards but only " + std::to_string(nDev) + " GPU(s) are visible");
-    const auto shards = cgi::splitReferenceGenomes((int)parameters.refSequences.size(), G);
+    const auto shards = cgi::splitReferenceGenomes((int)parameters.refSequences.size(), G, parameters.blockPartition);
     // the contexts (CUDA context creation, stream set-up) come up while the reader threads parse and pack the files
     std::vector<bani_ctx *> ctxs(G, nullptr); std::vector<std::string> ctxErr(G);
     std::vector<std::thread> ctxThreads;
@@ -331,7 +337,7 @@ int main(int argc, char **argv)
             if (g == 0) std::cerr << "INFO [GPU 0], skch::main, Time spent mapping " << qrySlot.size() << " query genome(s) : "
                                   << std::chrono::duration<double>(Clock::now() - t1).count() << " sec" << std::endl;
           }
-          cgi::correctRefGenomeIds(local, g, G);
+          cgi::correctRefGenomeIds(local, g, G, (int)parameters.refSequences.size(), parameters.blockPartition);
           std::lock_guard<std::mutex> l(mu);
           finalResults.insert(finalResults.end(), local.begin(), local.end());
         }

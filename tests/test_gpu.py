@@ -317,7 +317,7 @@ def test_cli_many_to_many_lists_match_the_python_host(tmp_path):
     m = open(tmp_path / "out.txt.matrix").read().splitlines()
     assert m[0] == str(len(genomes)) and m[1] == paths[0] and len(m) == 1 + len(genomes)
     # host CGI path (--visualize) gives the same table
-    _cli_run(["--ql", "ql.txt", "--rl", "rl.txt", "-o", "vis.txt", "--visualize", "--gpus", "1", "--minFraction", "0.1"], tmp_path)
+    _cli_run(["--ql", "ql.txt", "--rl", "rl.txt", "-o", "vis.txt", "--visualize", "--gpus", "1", "--minFraction", "0.1", "--partition", "block"], tmp_path)
     assert open(tmp_path / "vis.txt").read() == open(tmp_path / "out.txt").read()
 
 
