@@ -6,7 +6,7 @@
 // (Map::doL1Mapping, computeMap.hpp:260).
 //
 // The reference runs a monotone deque over the sequence.  The data-parallel statement of the
-// same function, verified record-for-record against the reference (tests/test_sketch_gpu.py):
+// same function, verified record-for-record against the reference (tests/test_gpu.py::test_sketch_edge_cases_vs_reference_golden, ::test_sketch_real_genomes_sha):
 //   hf(i), hb(i) = hash of the k-mer at i and of its reverse complement (ASCII bytes, seed 42)
 //   valid(i)     = hf(i) != hb(i)                                  (commonFunc.hpp:131)
 //   key(i)       = (min(hf,hb) << 32) | (0xFFFFFFFE - i)           valid positions only

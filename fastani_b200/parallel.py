@@ -72,35 +72,13 @@ def merge_shards(tables, n_queries, n_refs, world, partition="interleave"):
     return (cnt, idn) if tot is None else (cnt, idn, tot)
 
 
-def gather_rows(cgi_results, n_queries, n_refs, world, rank, dist=None, device=None, total_fragments=None, partition="interleave", out=None):
+def exchange_rows(cgi_results, world, rank, dist=None, device=None):
     """The result exchange of a multi-GPU run on the COMPACT rows: every rank contributes its cgi::CGI_Results rows
-    (20 bytes each; a few thousand per rank instead of a dense n_queries x n_refs / world table), one padded all-gather,
-    reference ids made global (correctRefGenomeIds), dense tables filled once.  Returns (count, identity, totals)."""
+    (20 bytes each; a few thousand per rank instead of a dense n_queries x n_refs / world table) to one padded all-gather.
+    Returns the per-rank row arrays (reference ids still shard-local), on every rank."""
     rows = np.ascontiguousarray(cgi_results)
-    if out is not None:                                      # reuse the caller's tables (no fresh 8 MB of pages per step)
-        cnt, idn, tot = out
-        cnt.fill(0); idn.fill(0); tot.fill(0)
-    else:
-        cnt = np.zeros((n_queries, n_refs), np.int32)
-        idn = np.zeros((n_queries, n_refs), np.float32)
-        tot = np.zeros(n_queries, np.int32)
-    if total_fragments is not None:
-        tot[:len(total_fragments)] = np.asarray(total_fragments, np.int64).astype(np.int32)
-
-    cflat, iflat = cnt.reshape(-1), idn.reshape(-1)
-
-    def fill(r, g):
-        if len(r):
-            w = r.view(np.int32).reshape(len(r), -1)             # columns: refGenomeId qryGenomeId countSeq totalQueryFragments identity-bits
-            q = w[:, 1].astype(np.int64)
-            flat = q * n_refs + global_ref_id(w[:, 0].astype(np.int64), world, g, n_refs, partition)
-            cflat[flat] = w[:, 2]
-            iflat[flat] = w[:, 4].view(np.float32)
-            np.maximum.at(tot, q, w[:, 3])
-
     if world == 1 or dist is None:
-        fill(rows, 0)
-        return cnt, idn, tot
+        return [rows]
     import torch
     n = torch.tensor([len(rows)], dtype=torch.int64, device=device if device is not None else "cpu")
     nall = torch.empty(world, dtype=torch.int64, device=n.device)
@@ -115,9 +93,37 @@ def gather_rows(cgi_results, n_queries, n_refs, world, rank, dist=None, device=N
     out = torch.empty((world * width, buf.shape[1]), dtype=t.dtype, device=t.device)
     dist.all_gather_into_tensor(out, t)
     o = out.cpu().numpy().reshape(world, width, buf.shape[1])
-    for g in range(world):
-        fill(np.ascontiguousarray(o[g, :ns[g]]).view(rows.dtype).reshape(-1), g)
+    return [np.ascontiguousarray(o[g, :ns[g]]).view(rows.dtype).reshape(-1) for g in range(world)]
+
+
+def rows_to_tables(parts, n_queries, n_refs, world, total_fragments=None, partition="interleave", out=None):
+    """Per-rank result rows (exchange_rows) -> dense (count, identity, totalQueryFragments) tables with global reference
+    ids (correctRefGenomeIds).  `out`: tables to reuse."""
+    if out is not None:
+        cnt, idn, tot = out
+        cnt.fill(0); idn.fill(0); tot.fill(0)
+    else:
+        cnt = np.zeros((n_queries, n_refs), np.int32)
+        idn = np.zeros((n_queries, n_refs), np.float32)
+        tot = np.zeros(n_queries, np.int32)
+    if total_fragments is not None:
+        tot[:len(total_fragments)] = np.asarray(total_fragments, np.int64).astype(np.int32)
+    cflat, iflat = cnt.reshape(-1), idn.reshape(-1)
+    for g, r in enumerate(parts):
+        if len(r):
+            w = np.ascontiguousarray(r).view(np.int32).reshape(len(r), -1)   # refGenomeId qryGenomeId countSeq totalQueryFragments identity-bits
+            q = w[:, 1].astype(np.int64)
+            flat = q * n_refs + global_ref_id(w[:, 0].astype(np.int64), world, g, n_refs, partition)
+            cflat[flat] = w[:, 2]
+            iflat[flat] = w[:, 4].view(np.float32)
+            np.maximum.at(tot, q, w[:, 3])
     return cnt, idn, tot
+
+
+def gather_rows(cgi_results, n_queries, n_refs, world, rank, dist=None, device=None, total_fragments=None, partition="interleave", out=None):
+    """exchange_rows + rows_to_tables: (count, identity, totals) with global ids on every rank."""
+    parts = exchange_rows(cgi_results, world, rank, dist, device)
+    return rows_to_tables(parts, n_queries, n_refs, world, total_fragments, partition, out)
 
 
 def gather_tables(cnt_local, idn_local, n_refs, world, rank, dist=None, device=None, tot=None, partition="interleave"):
