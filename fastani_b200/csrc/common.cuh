@@ -127,6 +127,7 @@ struct Ctx;
 // A piece holds at most 2^17 fragments of whole query genomes; arrays are packed back to back so that a
 // sketch can be exported to one flat device buffer and moved between GPUs.
 struct QPiece {
+  uint64_t memberOf = 0;             // uid of the index the fragment sketches were derived from (stage A'), 0 = hashed / imported
   int q0 = 0, nq = 0;                // local query range [q0, q0 + nq) of the owning sketch
   int32_t F = 0; uint64_t T = 0; int smax = 0;
   DevBuf<uint32_t> fragHash;         // T  : sorted unique hashes of fragment f at [segStart[f], segStart[f+1])
@@ -146,6 +147,7 @@ struct QSketch {
 
 // ---------------------------------------------------------------- index (HP1 output)
 struct Index {
+  uint64_t uid = next_genome_uid();  // identity of this index (a query sketch remembers the index it was derived from)
   int device = 0;
   uint64_t M = 0, U = 0, totalLen = 0;
   int32_t nContigs = 0, nGenomes = 0;

@@ -1077,6 +1077,7 @@ static QSketch *qsketch_build(Ctx *ctx, const std::vector<QuerySrc> &srcs, const
     if (F64 > 0x7ffffff0ll) fail(BANI_ERR_LIMIT, "a query genome has more than 2^31 fragments");
     auto pc = std::make_unique<QPiece>();
     pc->q0 = q0; pc->nq = q1 - q0; pc->F = (int32_t)F64;
+    pc->memberOf = (pieceFromIndex && hint) ? hint->uid : 0;
     qFragOff.push_back((int32_t)F64); pc->qFragOff = qFragOff;
     const int32_t F = pc->F;
     if (F > 0) {
@@ -1362,7 +1363,7 @@ static std::unique_ptr<QPiece> slice_piece(Ctx *ctx, const QPiece &pc, int qa, i
   cudaStream_t st = ctx->stream;
   auto sl = std::make_unique<QPiece>();
   const int32_t fA = pc.qFragOff[qa], fB = pc.qFragOff[qb];
-  sl->q0 = pc.q0 + qa; sl->nq = qb - qa; sl->F = fB - fA; sl->smax = pc.smax;
+  sl->q0 = pc.q0 + qa; sl->nq = qb - qa; sl->F = fB - fA; sl->smax = pc.smax; sl->memberOf = pc.memberOf;
   for (int q = qa; q <= qb; q++) sl->qFragOff.push_back(pc.qFragOff[q] - fA);
   if (sl->F > 0) {
     uint32_t tA = 0, tB = 0;
@@ -1452,9 +1453,11 @@ void qsketch_map(Ctx *ctx, const Index *ix, const QSketch *const *sketches, int3
         BANI_SCRATCH(uint32_t, hitCnt, T + 1);
         BANI_SCRATCH(unsigned long long, hitOff, T + 1);
         { Stage sg(ctx, "lookup", 12.0 * T);
+          // the membership filter pays when most probes miss: not for queries that are genomes of this very index
+          const bool useFilt = ix->filt.p && pc.memberOf != ix->uid;
           lookup_kernel<<<nblk(T + 1), 256, 0, st>>>(fragHash.p, (uint32_t)T, ix->tab.p, (1u << ix->tabBits) - 1u, ix->ukeys.p, ix->uoff.p,
-                                                   ix->dir.p, ix->dirBits, ix->filt.p, ix->filtBits ? (uint32_t)((1ull << ix->filtBits) - 1ull) : 0u,
-                                                   hitLo.p, hitCnt.p);
+                                                   ix->dir.p, ix->dirBits, useFilt ? ix->filt.p : nullptr,
+                                                   useFilt ? (uint32_t)((1ull << ix->filtBits) - 1ull) : 0u, hitLo.p, hitCnt.p);
           ctx->launches++;
           size_t tb = cub_scan_u64_temp(T + 1);
           BANI_SCRATCH(uint8_t, tmp, tb);
