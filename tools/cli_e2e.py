@@ -3,7 +3,7 @@
 import os, subprocess, sys, tempfile, time, shutil
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import fastani_b200 as fb
-import bench
+from fastani_b200 import workloads as W
 
 clusters = int(sys.argv[1]) if len(sys.argv) > 1 else 10
 strains = int(sys.argv[2]) if len(sys.argv) > 2 else 20
@@ -15,7 +15,7 @@ try:
     for c in range(clusters):
         for s in range(strains):
             p = os.path.join(tmp, "c%d_s%d.fna" % (c, s))
-            bench.write_fasta(p, "c%d_s%d" % (c, s), ctx.synth_genome(3, c + 1, s, 6000 * s, L))
+            W.write_fasta(p, [("c%d_s%d" % (c, s), ctx.synth_genome(3, c + 1, s, 6000 * s, L).tobytes())])
             paths.append(p)
     lst = os.path.join(tmp, "all.txt")
     open(lst, "w").write("\n".join(paths) + "\n")
