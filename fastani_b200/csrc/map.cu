@@ -826,24 +826,20 @@ __global__ void cgi_scatter_kernel(const CgiArgs a)
 
 // ordered float32 sum over the bins of one (query, genome) pair (computeCoreIdentity.hpp:267-297);
 // clears what it read so the table is all-zero again for the next chunk
-// (only the pairs that have mappings leave the device: one compact cgi::CGI_Results row each, in arbitrary order -- the
-//  host sorts the few thousand rows of a piece by (query, genome))
 __global__ void cgi_sum_kernel(uint32_t *table, uint8_t *touched, const uint32_t *contigBinOff, const int32_t *genomeContigEnd,
-                               unsigned long long totalBins, int nGenomes, int nQ, int qBase, bani_cgi_result *rowsOut, uint32_t *nRows)
+                               unsigned long long totalBins, int nGenomes, int nQ, int32_t *oCount, float *oIdent)
 {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (uint32_t)nQ * (uint32_t)nGenomes) return;
-  if (!touched[i]) return;
-  touched[i] = 0;
   const int q = i / nGenomes, g = i % nGenomes;
   int32_t cnt = 0; float sum = 0.0f;
-  const uint32_t b0 = contigBinOff[g ? genomeContigEnd[g - 1] : 0], b1 = contigBinOff[genomeContigEnd[g]];
-  uint32_t *row = table + (unsigned long long)q * totalBins;
-  for (uint32_t b = b0; b < b1; b++) { uint32_t v = row[b]; if (v) { sum += __uint_as_float(v); cnt++; row[b] = 0; } }
-  if (cnt > 0) {
-    bani_cgi_result r; r.refGenomeId = g; r.qryGenomeId = qBase + q; r.countSeq = cnt; r.totalQueryFragments = 0; r.identity = sum / cnt;
-    rowsOut[atomicAdd(nRows, 1u)] = r;
+  if (touched[i]) {
+    touched[i] = 0;
+    const uint32_t b0 = contigBinOff[g ? genomeContigEnd[g - 1] : 0], b1 = contigBinOff[genomeContigEnd[g]];
+    uint32_t *row = table + (unsigned long long)q * totalBins;
+    for (uint32_t b = b0; b < b1; b++) { uint32_t v = row[b]; if (v) { sum += __uint_as_float(v); cnt++; row[b] = 0; } }
   }
+  oCount[i] = cnt; oIdent[i] = cnt ? sum / cnt : 0.0f;
 }
 
 // ------------------------------------------------------------------ host orchestration
@@ -1442,7 +1438,8 @@ void qsketch_map(Ctx *ctx, const Index *ix, const QSketch *const *sketches, int3
     View<int32_t> d_fragQuery; d_fragQuery.p = pc.fragQuery.p; d_fragQuery.n = F;
     View<int32_t> d_fragSeqId; d_fragSeqId.p = pc.fragSeqId.p; d_fragSeqId.n = F;
 
-    std::vector<bani_cgi_result> pieceRows;                 // cgi::CGI_Results of this piece (qryGenomeId = query slot of the piece)
+    std::vector<int32_t> hCount; std::vector<float> hIdent;
+    if (wantCgi) { hCount.assign((size_t)nQc * nG, 0); hIdent.assign((size_t)nQc * nG, 0.f); }
 
     if (F > 0 && ix->M > 0) {
       ctx->upload_lut(smax, pc.sCount.p, F);
@@ -1696,11 +1693,8 @@ void qsketch_map(Ctx *ctx, const Index *ix, const QSketch *const *sketches, int3
                 CgiArgs ca; ca.rows = rows.p; ca.rFrag = rFrag.p; ca.R = R; ca.fragQuery = d_fragQuery.p;
                 ca.contigGenome = ix->contigGenome.p; ca.contigBinOff = ix->contigBinOff.p; ca.fragLen = fragLen;
                 ca.totalBins = ix->totalBins; ca.nGenomes = nG; ca.table = table.p; ca.touched = touched.p;
-                // a (query, genome) pair has a row only if a mapping of the piece touched it: R bounds the rows
-                const size_t rowCap = std::min<size_t>((size_t)nQc * nG, (size_t)R);
-                BANI_SCRATCH(bani_cgi_result, d_cgi, rowCap);
-                BANI_SCRATCH(uint32_t, d_nCgi, 1);
-                BANI_CUDA(cudaMemsetAsync(d_nCgi.p, 0, 4, st));
+                BANI_SCRATCH(int32_t, oCount, (size_t)nQc * nG);
+                DevBuf<float> oIdent((size_t)nQc * nG, st);
                 { Stage sg(ctx, "cgi", 48.0 * R);
                   for (int qa = 0; qa < nQc; qa += (int)tableQ) {
                     const int nPass = std::min<int>((int)tableQ, nQc - qa);
@@ -1708,15 +1702,11 @@ void qsketch_map(Ctx *ctx, const Index *ix, const QSketch *const *sketches, int3
                     cgi_scatter_kernel<<<nblk(R), 256, 0, st>>>(ca);
                     ctx->launches++;
                     cgi_sum_kernel<<<nblk((uint64_t)nPass * nG), 256, 0, st>>>(table.p, touched.p, ix->contigBinOff.p, d_gce.p,
-                                                                             ix->totalBins, nG, nPass, qa, d_cgi.p, d_nCgi.p);
+                                                                             ix->totalBins, nG, nPass, oCount.p + (size_t)qa * nG, oIdent.p + (size_t)qa * nG);
                     ctx->launches++;
                   } }
-                uint32_t nCgi = 0;
-                BANI_CUDA(cudaMemcpyAsync(&nCgi, d_nCgi.p, 4, cudaMemcpyDeviceToHost, st));
-                BANI_CUDA(cudaStreamSynchronize(st));
-                if (nCgi > rowCap) fail(BANI_ERR_INTERNAL, "more identity rows than mappings");
-                pieceRows.resize(nCgi);
-                if (nCgi) BANI_CUDA(cudaMemcpyAsync(pieceRows.data(), d_cgi.p, sizeof(bani_cgi_result) * (size_t)nCgi, cudaMemcpyDeviceToHost, st));
+                BANI_CUDA(cudaMemcpyAsync(hCount.data(), oCount.p, 4 * (size_t)nQc * nG, cudaMemcpyDeviceToHost, st));
+                BANI_CUDA(cudaMemcpyAsync(hIdent.data(), oIdent.p, 4 * (size_t)nQc * nG, cudaMemcpyDeviceToHost, st));
                 BANI_CUDA(cudaStreamSynchronize(st));
               }
             }
@@ -1728,14 +1718,16 @@ void qsketch_map(Ctx *ctx, const Index *ix, const QSketch *const *sketches, int3
     }
     if (!split) { out.ctr.fragments += F; out.ctr.sum_s += (F > 0 && ix->M > 0) ? T : 0; }
     if (wantCgi && !split) {
-      std::sort(pieceRows.begin(), pieceRows.end(), [](const bani_cgi_result &x, const bani_cgi_result &y) {
-        return x.qryGenomeId != y.qryGenomeId ? x.qryGenomeId < y.qryGenomeId : x.refGenomeId < y.refGenomeId; });
-      for (bani_cgi_result r : pieceRows) {
-        const int q = r.qryGenomeId;                                               // query slot of the piece
-        r.qryGenomeId = qs->queryId[q0 + q];
-        r.totalQueryFragments = (int32_t)qs->totalFragments[q0 + q];               // cgid_types.hpp:73 (int)
-        out.cgi.push_back(r);
-      }
+      for (int q = 0; q < nQc; q++)
+        for (int g = 0; g < nG; g++) {
+          const int32_t cnt = hCount[(size_t)q * nG + g];
+          if (cnt > 0) {
+            bani_cgi_result r; r.refGenomeId = g; r.qryGenomeId = qs->queryId[q0 + q]; r.countSeq = cnt;
+            r.totalQueryFragments = (int32_t)qs->totalFragments[q0 + q];            // cgid_types.hpp:73 (int)
+            r.identity = hIdent[(size_t)q * nG + g];
+            out.cgi.push_back(r);
+          }
+        }
     }
    }
   }
