@@ -93,6 +93,7 @@ int bani_ctx_create(int device, const bani_params *p, bani_ctx **out)
     if (const char *e = getenv("BANI_MAX_HITS_PER_PIECE")) f.maxHitsPerPiece = std::max(1ll, atoll(e));
     if (const char *e = getenv("BANI_FRAG_L1_MAX")) f.fragL1Max = std::max(0ll, atoll(e));
     if (const char *e = getenv("BANI_L2_STAGE")) f.l2Stage = atoi(e) != 0;
+    if (const char *e = getenv("BANI_TRACE")) f.trace = atoi(e) != 0;
     if (const char *e = getenv("BANI_L2E_BUCKETS")) { const int v = atoi(e); if (v == 1024 || v == 4096) f.l2eBuckets = v; }
   }
   dev_cache_flush(device);                   // blocks cached under streams of destroyed contexts
@@ -306,6 +307,7 @@ int bani_index_build(bani_ctx *ctx, bani_genome *const *refs, int32_t n_refs, ba
   BANI_TRY
   if (!ctx || !out || n_refs < 0 || (n_refs && !refs)) fail(BANI_ERR_ARG, "null argument");
   BANI_CUDA(cudaSetDevice(ctx->c.device));
+  ctx->c.mark("index_build: called");
   std::vector<Genome *> gs(n_refs);
   for (int i = 0; i < n_refs; i++) { if (!refs[i]) fail(BANI_ERR_ARG, "null genome handle"); gs[i] = &refs[i]->g; }
   Index *ix = index_build(&ctx->c, gs.data(), n_refs);
@@ -449,7 +451,9 @@ int bani_map_cgi(bani_ctx *ctx, const bani_index *ix, bani_genome *const *querie
   std::vector<const Genome *> qs(n_queries);
   for (int i = 0; i < n_queries; i++) { if (!queries[i]) fail(BANI_ERR_ARG, "null genome handle"); qs[i] = &queries[i]->g; }
   MapOutput mo;
+  ctx->c.mark("map_cgi: enter");
   map_queries(&ctx->c, ix->ix, qs.data(), n_queries, false, true, mo);
+  ctx->c.mark("map_cgi: map_queries returned");
   *n_results = mo.cgi.size();
   *results = nullptr;
   if (!mo.cgi.empty()) {
@@ -459,6 +463,7 @@ int bani_map_cgi(bani_ctx *ctx, const bani_index *ix, bani_genome *const *querie
   }
   if (total_query_fragments) for (int i = 0; i < n_queries; i++) total_query_fragments[i] = mo.totalQueryFragments[i];
   if (counters) *counters = mo.ctr;
+  ctx->c.mark("map_cgi: results copied");
   return BANI_OK;
   BANI_CATCH
 }

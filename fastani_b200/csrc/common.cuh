@@ -9,6 +9,7 @@
 #include <stdexcept>
 #include <cstdio>
 #include <cstdarg>
+#include <chrono>
 #include "../../include/fastani_b200.h"
 
 namespace bani {
@@ -196,12 +197,13 @@ struct View {
 };
 
 // Run-time switches of a context (bani_ctx_set_flag); the defaults can also be set through the environment
-// (BANI_NO_SKETCH_REUSE, BANI_MAX_HITS_PER_PIECE, BANI_FRAG_L1_MAX, BANI_L2E_BUCKETS, BANI_L2_STAGE), read when the context is created.
+// (BANI_NO_SKETCH_REUSE, BANI_MAX_HITS_PER_PIECE, BANI_FRAG_L1_MAX, BANI_L2E_BUCKETS, BANI_L2_STAGE, BANI_TRACE), read when the context is created.
 struct CtxFlags {
   int sketchReuse = 1;                        // stage A': fragment sketches of index members are read from the index
   long long maxHitsPerPiece = 3ll << 29;      // a piece that gathers more index hits is split at a query boundary
   long long fragL1Max = 8192;                 // hits per fragment handled inside one CTA (<= FRAG_L1_MAX)
   int l2eBuckets = 0;                         // 0 = adaptive; 1024 / 4096 force the size of the L2 rank directory
+  int trace = 0;                              // BANI_TRACE: wall-clock marks of the host orchestration on stderr (diagnostic)
   int l2Stage = 0;                            // 1: l2_events_kernel stages event codes in shared memory where the window links allow it
                                               //    (measured slower than the direct stores on B200: DESIGN.md section 6; kept as a tested alternative)
   long long uploadGroupWords = 16ll << 20;    // packed words (16 bases each) per upload group of the host-packed ingest
@@ -219,6 +221,15 @@ struct Ctx {
   int lutUploaded = 0;
   void upload_lut(int smax, const int32_t *d_sCount = nullptr, int32_t F = 0);
   // optional per-stage device timing (CUDA events on `stream`), see bani_ctx_profile_*
+  // diagnostic: microseconds of host wall clock since the previous mark (flags.trace)
+  std::chrono::steady_clock::time_point traceT = std::chrono::steady_clock::now();
+  void mark(const char *what)
+  {
+    if (!flags.trace) return;
+    const auto t = std::chrono::steady_clock::now();
+    fprintf(stderr, "[bani trace] %-28s +%8.1f us\n", what, std::chrono::duration<double, std::micro>(t - traceT).count());
+    traceT = t;
+  }
   uint64_t launches = 0;             // kernels of this library launched so far (CUB's not counted)
   bool profiling = false;
   struct ProfEv { const char *name; cudaEvent_t a, b; double bytes; };

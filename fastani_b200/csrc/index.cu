@@ -315,7 +315,9 @@ Index *index_build(Ctx *ctx, Genome *const *refs, int32_t nRefs)
     ix->seqsByFile.push_back((int32_t)desc.size());
   }
   const int32_t nC = (int32_t)desc.size();
+  ctx->mark("index_build: enter + contig loop");
   const unsigned long long totalBits = index_contig_tables(ctx, ix.get(), contigGenome);
+  ctx->mark("index_build: contig tables");
 
   if (nC == 0 || totalPos == 0) { index_make_empty(ctx, ix.get()); return ix.release(); }
 
@@ -356,6 +358,7 @@ Index *index_build(Ctx *ctx, Genome *const *refs, int32_t nRefs)
         if (M > 0xfffffff0ull) fail(BANI_ERR_LIMIT, "more than 2^32 minimizers in one index shard");
       }
       sg.bytes((double)ix->totalLen / 4.0 + 12.0 * (double)M);       // packed bases in, 12-byte records out
+      ctx->mark("index_build: sketched");
       if (M <= cap) break;
       cap = M;
     }
@@ -368,6 +371,7 @@ Index *index_build(Ctx *ctx, Genome *const *refs, int32_t nRefs)
     BANI_CUDA(cudaMemcpyAsync(ix->seqId.p, ts.p, 4 * M, cudaMemcpyDeviceToDevice, st));
   }
   index_finish(ctx, ix.get());
+  ctx->mark("index_build: finished");
   return ix.release();
 }
 

@@ -31,6 +31,7 @@
 //   H  CGI         1-way best per (fragment, genome); 2-way best per (ref contig, position bin) via
 //                  atomicMax on a dense bin table; ordered float32 sum per genome pair
 #include "common.cuh"
+#include "cgi_rows.hpp"
 #include <algorithm>
 #include <cstring>
 #include <deque>
@@ -1385,9 +1386,13 @@ void map_queries(Ctx *ctx, const Index *ix, const Genome *const *queries, int32_
                  bool wantRows, bool wantCgi, MapOutput &out)
 {
   std::unique_ptr<QSketch> qs(qsketch_create(ctx, queries, nq, nullptr, ix));
+  ctx->mark("map: query sketches built");
   const QSketch *one = qs.get();
   qsketch_map(ctx, ix, &one, 1, wantRows, wantCgi, out);
+  ctx->mark("map: qsketch_map returned");
   out.totalQueryFragments = qs->totalFragments;
+  qs.reset();
+  ctx->mark("map: query sketches freed");
 }
 
 void qsketch_map(Ctx *ctx, const Index *ix, const QSketch *const *sketches, int32_t nSketches,
@@ -1441,6 +1446,7 @@ void qsketch_map(Ctx *ctx, const Index *ix, const QSketch *const *sketches, int3
     std::vector<int32_t> hCount; std::vector<float> hIdent;
     if (wantCgi) { hCount.assign((size_t)nQc * nG, 0); hIdent.assign((size_t)nQc * nG, 0.f); }
 
+    ctx->mark("piece: begin");
     if (F > 0 && ix->M > 0) {
       ctx->upload_lut(smax, pc.sCount.p, F);
 
@@ -1462,6 +1468,7 @@ void qsketch_map(Ctx *ctx, const Index *ix, const QSketch *const *sketches, int3
         unsigned long long N = 0;
         BANI_CUDA(cudaMemcpyAsync(&N, hitOff.p + T, 8, cudaMemcpyDeviceToHost, st));
         BANI_CUDA(cudaStreamSynchronize(st));
+        ctx->mark("piece: lookup done");
         if (N > maxHits && nQc > 1) {
           // too many hits for one pass: halve the piece at a query boundary (by fragments) and do the halves instead
           int qm = 1;
@@ -1670,6 +1677,7 @@ void qsketch_map(Ctx *ctx, const Index *ix, const QSketch *const *sketches, int3
             BANI_CUDA(cudaMemcpyAsync(&n2, d_n2.p, 8, cudaMemcpyDeviceToHost, st));
             BANI_CUDA(cudaStreamSynchronize(st));
             out.ctr.n2 += n2; out.ctr.mappings += R;
+            ctx->mark("piece: L1 + L2 done");
             Stage::set_bytes(ctx, idEv, 16.0 * (double)n2 + evBytes);   // 16-byte records in, 2-byte event codes out
             if (R > 0) {
               BANI_SCRATCH(bani_mapping, rows, R);
@@ -1705,9 +1713,11 @@ void qsketch_map(Ctx *ctx, const Index *ix, const QSketch *const *sketches, int3
                                                                              ix->totalBins, nG, nPass, oCount.p + (size_t)qa * nG, oIdent.p + (size_t)qa * nG);
                     ctx->launches++;
                   } }
+                ctx->mark("piece: cgi launched");
                 BANI_CUDA(cudaMemcpyAsync(hCount.data(), oCount.p, 4 * (size_t)nQc * nG, cudaMemcpyDeviceToHost, st));
                 BANI_CUDA(cudaMemcpyAsync(hIdent.data(), oIdent.p, 4 * (size_t)nQc * nG, cudaMemcpyDeviceToHost, st));
                 BANI_CUDA(cudaStreamSynchronize(st));
+                ctx->mark("piece: identity tables on host");
               }
             }
           }
@@ -1718,19 +1728,12 @@ void qsketch_map(Ctx *ctx, const Index *ix, const QSketch *const *sketches, int3
     }
     if (!split) { out.ctr.fragments += F; out.ctr.sum_s += (F > 0 && ix->M > 0) ? T : 0; }
     if (wantCgi && !split) {
-      for (int q = 0; q < nQc; q++)
-        for (int g = 0; g < nG; g++) {
-          const int32_t cnt = hCount[(size_t)q * nG + g];
-          if (cnt > 0) {
-            bani_cgi_result r; r.refGenomeId = g; r.qryGenomeId = qs->queryId[q0 + q]; r.countSeq = cnt;
-            r.totalQueryFragments = (int32_t)qs->totalFragments[q0 + q];            // cgid_types.hpp:73 (int)
-            r.identity = hIdent[(size_t)q * nG + g];
-            out.cgi.push_back(r);
-          }
-        }
+      append_cgi_rows(hCount.data(), hIdent.data(), nQc, nG, qs->queryId.data() + q0, qs->totalFragments.data() + q0, out.cgi);
     }
+    ctx->mark("piece: rows assembled");
    }
   }
+  ctx->mark("qsketch_map: pieces done");
 }
 
 } // namespace bani

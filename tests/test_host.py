@@ -234,3 +234,52 @@ def test_host_packer_matches_the_reference_bytes():
     b1, b2 = fb.PackedBatch(gl), fb.PackedBatch(gl, threads=3)
     assert (b1.word_off % 4 == 0).all() and list(b1.gen_off) == [0, 3, 3, 4] and list(b1.contig_len[:4]) == [5000, 0, 4001, 8]
     assert (b1.words == b2.words).all() and (b1.exc_pos == b2.exc_pos).all() and (b1.exc_off == b2.exc_off).all()
+
+
+def test_records_leave_c_buffers_in_one_copy():
+    """api._records_from: the structured rows of a C result buffer, bit for bit (replaces a per-field numpy copy)."""
+    import ctypes as C
+    from fastani_b200 import api
+    rng = np.random.default_rng(5)
+    for dt in (api.CGI_DTYPE, api.MAPPING_DTYPE):
+        for n in (0, 1, 777):
+            src = np.frombuffer(rng.integers(0, 256, n * dt.itemsize, dtype=np.uint8).tobytes(), dtype=dt)
+            buf = C.create_string_buffer(src.tobytes(), max(n * dt.itemsize, 1))
+            got = api._records_from(C.addressof(buf), n, dt)
+            assert got.dtype == dt and got.flags.writeable and got.tobytes() == src.tobytes()
+
+
+def test_identity_rows_from_dense_tables(tmp_path):
+    """csrc/cgi_rows.hpp (host part of the reduction: dense count / identity tables -> cgi::CGI_Results rows, zeros skipped
+    four at a time) against the plain double loop, on ragged table widths."""
+    import subprocess
+    src = tmp_path / "t.cpp"
+    src.write_text(r'''
+#include "cgi_rows.hpp"
+#include <cstdio>
+#include <random>
+int main() {
+  std::mt19937 rng(7);
+  for (int nG : {0, 1, 2, 3, 4, 5, 7, 8, 9, 63, 1000}) for (int nQ : {0, 1, 3, 17}) for (int dens : {0, 1, 30, 100}) {
+    std::vector<int32_t> cnt((size_t)nQ * nG); std::vector<float> idn((size_t)nQ * nG);
+    for (size_t i = 0; i < cnt.size(); i++) { const bool on = (int)(rng() % 100) < dens; cnt[i] = on ? 1 + (int)(rng() % 1666) : 0; idn[i] = on ? 80.f + (rng() % 2000) / 100.f : 0.f; }
+    std::vector<int32_t> qid(nQ); std::vector<uint64_t> tot(nQ);
+    for (int q = 0; q < nQ; q++) { qid[q] = 1000 - q; tot[q] = 1600 + q; }
+    std::vector<bani_cgi_result> got, want;
+    bani::append_cgi_rows(cnt.data(), idn.data(), nQ, nG, qid.data(), tot.data(), got);
+    for (int q = 0; q < nQ; q++) for (int g = 0; g < nG; g++) if (cnt[(size_t)q * nG + g] > 0) {
+      bani_cgi_result r; r.refGenomeId = g; r.qryGenomeId = qid[q]; r.countSeq = cnt[(size_t)q * nG + g]; r.totalQueryFragments = (int32_t)tot[q]; r.identity = idn[(size_t)q * nG + g];
+      want.push_back(r); }
+    if (got.size() != want.size()) { printf("size %zu %zu nG %d nQ %d\\n", got.size(), want.size(), nG, nQ); return 1; }
+    for (size_t i = 0; i < got.size(); i++) if (memcmp(&got[i], &want[i], sizeof got[i])) { printf("row %zu differs\\n", i); return 1; }
+  }
+  puts("ok");
+  return 0;
+}
+''')
+    exe = tmp_path / "t"
+    inc = os.path.join(ROOT, "fastani_b200", "csrc")
+    r = subprocess.run(["g++", "-O2", "-std=c++17", "-I", inc, str(src), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stdout
