@@ -116,7 +116,10 @@ BANI_API void *bani_ctx_stream(bani_ctx *ctx);
 
 /* Run-time switches of a context.  name: "sketch_reuse" (1 = read the fragment sketches of index members from the
  * index, 0 = always hash the query fragments: what a run with --ql != --rl does), "max_hits_per_piece",
- * "frag_l1_max", "l2e_buckets", "l2_stage", "upload_group_words" (tuning / test switches; results never depend on them). */
+ * "frag_l1_max", "l2e_buckets", "l2_stage", "upload_group_words" (tuning / test switches; results never depend on them).
+ * Environment, read when a context is created: BANI_NO_SKETCH_REUSE, BANI_MAX_HITS_PER_PIECE, BANI_FRAG_L1_MAX,
+ * BANI_L2E_BUCKETS, BANI_L2_STAGE set the defaults of those switches; BANI_TRACE=1 prints the host wall clock between
+ * marks of the orchestration (index build, query sketches, every piece of the mapping) on stderr. */
 BANI_API int  bani_ctx_set_flag(bani_ctx *ctx, const char *name, int64_t value);
 
 /* Per-stage device timing.  When enabled, every stage of HP1/HP2 is bracketed by CUDA events on
