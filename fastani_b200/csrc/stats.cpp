@@ -10,40 +10,56 @@
 // transcendental calls, float narrowing on return); see the comments per function.
 // GSL's gsl_cdf_binomial_Q (third party, not vendored by the reference) is replaced
 // by its definition: the upper tail of the binomial distribution.
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
-#include <vector>
+#include <cstring>
+#include <map>
+#include <memory>
 #include <mutex>
+#include <thread>
+#include <tuple>
+#include <vector>
 #include "common.cuh"
 
 namespace bani {
 
 namespace {
 
-// log-factorial table, grown on demand
-std::vector<long double> g_lfact;
+// log-factorial table: filled once, read-only afterwards (the LUT rows are computed by several threads)
+constexpr int LFACT_N = 65600;                 // covers sketch sizes up to fragLen = 60000 (the largest the ABI accepts)
 std::mutex g_mu;
 
-const long double *lfact_upto(int n)
+const long double *lfact_table()
 {
-  if ((int)g_lfact.size() <= n) {
-    size_t old = g_lfact.size();
-    g_lfact.resize(n + 64);
-    for (size_t i = old; i < g_lfact.size(); i++) g_lfact[i] = (i == 0) ? 0.0L : g_lfact[i - 1] + logl((long double)i);
-  }
-  return g_lfact.data();
+  static std::once_flag once;
+  static std::vector<long double> tab;
+  std::call_once(once, [] {
+    tab.resize(LFACT_N);
+    tab[0] = 0.0L;
+    for (int i = 1; i < LFACT_N; i++) tab[i] = tab[i - 1] + logl((long double)i);
+  });
+  return tab.data();
 }
 
-// tails[y] = P[X >= y], X ~ Bin(n, p), for y = 0..n+1   (tails[n+1] = 0)
-void binomial_upper_tails(int n, double p, std::vector<long double> &tails)
+// tails[y] = P[X >= y], X ~ Bin(n, p), for y = lowest..n+1   (tails[n+1] = 0; entries below `lowest` are not computed:
+// the sum runs downwards from n, so the entries that are computed do not depend on where it stops)
+void binomial_upper_tails(int n, double p, std::vector<long double> &tails, int lowest = 0)
 {
   tails.assign(n + 2, 0.0L);
+  if (lowest < 0) lowest = 0;
   if (p <= 0.0) { tails[0] = 1.0L; return; }
   if (p >= 1.0) { for (int y = 0; y <= n; y++) tails[y] = 1.0L; return; }
-  const long double *lf = lfact_upto(n + 1);
+  std::vector<long double> own;
+  const long double *lf = lfact_table();
+  if (n + 1 >= LFACT_N) {                      // beyond the shared table: a private one (slow, correct)
+    own.resize((size_t)n + 2); own[0] = 0.0L;
+    for (int i = 1; i <= n + 1; i++) own[i] = own[i - 1] + logl((long double)i);
+    lf = own.data();
+  }
   long double lp = logl((long double)p), lq = log1pl(-(long double)p);
   long double acc = 0.0L;
-  for (int i = n; i >= 0; i--) {
+  for (int i = n; i >= lowest; i--) {
     acc += expl(lf[n] - lf[i] - lf[n - i] + (long double)i * lp + (long double)(n - i) * lq);
     tails[i] = acc > 1.0L ? 1.0L : acc;
   }
@@ -53,9 +69,8 @@ void binomial_upper_tails(int n, double p, std::vector<long double> &tails)
 double binomial_Q(unsigned k, double p, unsigned n)
 {
   if (k >= n) return 0.0;
-  std::lock_guard<std::mutex> lk(g_mu);
   std::vector<long double> t;
-  binomial_upper_tails((int)n, p, t);
+  binomial_upper_tails((int)n, p, t, (int)k + 1);
   return (double)t[k + 1];
 }
 
@@ -85,7 +100,7 @@ float md_lower_bound(float d, int s, int k, float ci, std::vector<long double> &
   int x = (int)std::ceil((double)sj);
   if (x < 1) x = 1;
   if (x <= s) {
-    binomial_upper_tails(s, (double)pj, scratch);
+    binomial_upper_tails(s, (double)pj, scratch, x);       // the loop below reads entries x, x+1, ... only
     while (x <= s) {
       double cdf_complement = (double)scratch[x];          // P[X > x-1] = P[X >= x]
       if (cdf_complement < q2) { x--; break; }
@@ -109,7 +124,6 @@ int min_hits(int s, int k, float perc_identity)
 // map_stats.hpp:142-167
 int stat_min_hits_relaxed(int s, int k, float perc_identity)
 {
-  std::lock_guard<std::mutex> lk(g_mu);
   std::vector<long double> scratch;
   int first = min_hits(s, k, perc_identity);
   int relaxed = first;
@@ -134,7 +148,6 @@ static void identity_nolock(int shared, int s, int k, float *id, float *ub, std:
 
 void stat_identity(int shared, int s, int k, float *id, float *ub)
 {
-  std::lock_guard<std::mutex> lk(g_mu);
   std::vector<long double> scratch;
   identity_nolock(shared, s, k, id, ub, scratch);
 }
@@ -163,38 +176,94 @@ int stat_recommended_window_size(double p_value, int k, float identity, int frag
   return std::min(std::max(w, 1), fragLen);
 }
 
-static void lut_row(StatLut &L, int s, std::vector<long double> &scratch, int32_t &minHitsOut, std::vector<float> &idRow, std::vector<float> &ubRow)
+// One row of the table: pure function of (s, k, pid)
+struct LutRow { int32_t minHits = 1; std::vector<float> ident, upper; };
+
+static void lut_row(int k, float pid, int s, std::vector<long double> &scratch, LutRow &row)
 {
   // estimateMinimumHitsRelaxed + the max(1, .) of computeL1CandidateRegions (computeMap.hpp:316-317)
-  int first = min_hits(s, L.k, L.pid);
+  int first = min_hits(s, k, pid);
   int relaxed = first;
   for (int i = first; i >= 0; i--) {
     float jaccard = 1.0 * i / s;
-    float d = j2md(jaccard, L.k);
-    float d_lower = md_lower_bound(d, s, L.k, 0.9, scratch);
+    float d = j2md(jaccard, k);
+    float d_lower = md_lower_bound(d, s, k, 0.9, scratch);
     float id_upper = 100.0 * (1.0 - d_lower);
-    if (id_upper >= L.pid) relaxed = i; else break;
+    if (id_upper >= pid) relaxed = i; else break;
   }
-  minHitsOut = relaxed < 1 ? 1 : relaxed;
-  idRow.resize(s + 1); ubRow.resize(s + 1);
-  for (int x = 0; x <= s; x++) identity_nolock(x, s, L.k, &idRow[x], &ubRow[x], scratch);
+  row.minHits = relaxed < 1 ? 1 : relaxed;
+  row.ident.resize(s + 1); row.upper.resize(s + 1);
+  for (int x = 0; x <= s; x++) identity_nolock(x, s, k, &row.ident[x], &row.upper[x], scratch);
 }
+
+// Rows are shared by every context of the process (the command line drives one context per GPU; a row costs O(s^2) tail
+// terms: ~0.6 s for the 320 rows of the default parameters on one core).  Missing rows are computed by a few threads.
+namespace {
+struct RowKey {
+  int k; uint32_t pidBits; int s;
+  bool operator<(const RowKey &o) const { return std::tie(k, pidBits, s) < std::tie(o.k, o.pidBits, o.s); }
+};
+std::map<RowKey, std::shared_ptr<const LutRow>> g_rows;      // guarded by g_mu
+
+uint32_t float_bits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+
+// rows for the sketch sizes `want` (each >= 1), in that order; g_mu held by the caller
+std::vector<std::shared_ptr<const LutRow>> rows_for(int k, float pid, const std::vector<int> &want)
+{
+  const uint32_t pb = float_bits(pid);
+  std::vector<std::shared_ptr<const LutRow>> out(want.size());
+  std::vector<size_t> missing;
+  for (size_t i = 0; i < want.size(); i++) {
+    auto it = g_rows.find(RowKey{k, pb, want[i]});
+    if (it != g_rows.end()) out[i] = it->second; else missing.push_back(i);
+  }
+  if (!missing.empty()) {
+    (void)lfact_table();
+    std::vector<std::shared_ptr<LutRow>> made(missing.size());
+    unsigned hw = std::thread::hardware_concurrency();
+    size_t nt = std::min<size_t>(std::min<size_t>(hw ? hw : 1, 16), missing.size());
+    // a row of size s costs ~s^2: deal the rows round-robin in decreasing size so the threads finish together
+    std::vector<size_t> order(missing.size());
+    for (size_t i = 0; i < order.size(); i++) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return want[missing[a]] > want[missing[b]]; });
+    auto work = [&](size_t t) {
+      std::vector<long double> scratch;
+      for (size_t j = t; j < order.size(); j += nt) {
+        auto r = std::make_shared<LutRow>();
+        lut_row(k, pid, want[missing[order[j]]], scratch, *r);
+        made[order[j]] = std::move(r);
+      }
+    };
+    if (nt <= 1) work(0);
+    else {
+      std::vector<std::thread> th;
+      for (size_t t = 1; t < nt; t++) th.emplace_back(work, t);
+      work(0);
+      for (auto &x : th) x.join();
+    }
+    for (size_t j = 0; j < missing.size(); j++) {
+      out[missing[j]] = made[j];
+      g_rows[RowKey{k, pb, want[missing[j]]}] = made[j];
+    }
+  }
+  return out;
+}
+} // namespace
 
 void StatLut::ensure(int s_needed)
 {
   if (s_needed <= smax) return;
   std::lock_guard<std::mutex> lk(g_mu);
-  std::vector<long double> scratch;
   if (minHits.empty()) { minHits.push_back(1); rowOff.push_back(0); ident.push_back(0.f); upper.push_back(0.f); have.push_back(1); }  // s = 0 row (unused)
   if ((int)minHits.size() < s_needed + 1) { minHits.resize(s_needed + 1, 1); rowOff.resize(s_needed + 1, 0); have.resize(s_needed + 1, 0); }
-  std::vector<float> idRow, ubRow;
-  for (int s = smax + 1; s <= s_needed; s++) {
-    if (have[s]) continue;
-    int32_t mh;
-    lut_row(*this, s, scratch, mh, idRow, ubRow);
-    minHits[s] = mh;
+  std::vector<int> want;
+  for (int s = smax + 1; s <= s_needed; s++) if (!have[s]) want.push_back(s);
+  const auto rows = rows_for(k, pid, want);
+  for (size_t i = 0; i < want.size(); i++) {
+    const int s = want[i];
+    minHits[s] = rows[i]->minHits;
     rowOff[s] = (uint32_t)ident.size();
-    ident.insert(ident.end(), idRow.begin(), idRow.end()); upper.insert(upper.end(), ubRow.begin(), ubRow.end());
+    ident.insert(ident.end(), rows[i]->ident.begin(), rows[i]->ident.end()); upper.insert(upper.end(), rows[i]->upper.begin(), rows[i]->upper.end());
     have[s] = 1;
   }
   smax = s_needed;
@@ -205,23 +274,23 @@ void StatLut::ensure(int s_needed)
 bool StatLut::ensure_rows(const std::vector<int> &svals)
 {
   std::lock_guard<std::mutex> lk(g_mu);
-  std::vector<long double> scratch;
   if (minHits.empty()) { minHits.push_back(1); rowOff.push_back(0); ident.push_back(0.f); upper.push_back(0.f); have.push_back(1); }
-  bool added = false;
-  std::vector<float> idRow, ubRow;
+  std::vector<int> want;
   for (int s : svals) {
     if (s < 1) continue;
     if ((int)minHits.size() < s + 1) { minHits.resize(s + 1, 1); rowOff.resize(s + 1, 0); have.resize(s + 1, 0); }
-    if (have[s]) continue;
-    int32_t mh;
-    lut_row(*this, s, scratch, mh, idRow, ubRow);
-    minHits[s] = mh;
-    rowOff[s] = (uint32_t)ident.size();
-    ident.insert(ident.end(), idRow.begin(), idRow.end()); upper.insert(upper.end(), ubRow.begin(), ubRow.end());
-    have[s] = 1;
-    added = true;
+    if (have[s] || std::find(want.begin(), want.end(), s) != want.end()) continue;
+    want.push_back(s);
   }
-  return added;
+  const auto rows = rows_for(k, pid, want);
+  for (size_t i = 0; i < want.size(); i++) {
+    const int s = want[i];
+    minHits[s] = rows[i]->minHits;
+    rowOff[s] = (uint32_t)ident.size();
+    ident.insert(ident.end(), rows[i]->ident.begin(), rows[i]->ident.end()); upper.insert(upper.end(), rows[i]->upper.begin(), rows[i]->upper.end());
+    have[s] = 1;
+  }
+  return !want.empty();
 }
 
 } // namespace bani

@@ -283,3 +283,45 @@ int main() {
     assert r.returncode == 0, r.stderr
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.strip() == "ok", r.stdout
+
+
+def test_statistic_lut_rows_equal_the_scalar_functions(tmp_path):
+    """StatLut (csrc/stats.cpp: rows computed by several threads, shared by the contexts of a process, binomial tails only as
+    deep as they are read) against bani_stat_identity / bani_stat_min_hits_relaxed, which the goldens above pin to the reference."""
+    import subprocess
+    cuda_inc = "/usr/local/cuda/include"
+    if not os.path.exists(os.path.join(cuda_inc, "cuda_runtime.h")):
+        pytest.skip("CUDA headers not found")
+    src = tmp_path / "t.cpp"
+    src.write_text(r'''#include "common.cuh"
+#include <cstdio>
+#include <cstring>
+using namespace bani;
+static int check(const StatLut &l, int s, int k, float pid) {
+  if (!l.have[s]) { printf("row %d missing\\n", s); return 1; }
+  if (l.minHits[s] != std::max(1, stat_min_hits_relaxed(s, k, pid))) { printf("minHits %d\\n", s); return 1; }
+  for (int x = 0; x <= s; x++) { float a, b; stat_identity(x, s, k, &a, &b);
+    if (memcmp(&a, &l.ident[l.rowOff[s] + x], 4) || memcmp(&b, &l.upper[l.rowOff[s] + x], 4)) { printf("row %d x %d\\n", s, x); return 1; } }
+  return 0;
+}
+int main() {
+  for (int k : {16, 21}) {
+    StatLut l; l.k = k; l.pid = 80.0f;
+    l.ensure(97); l.ensure(130);
+    for (int s = 1; s <= 130; s++) if (check(l, s, k, 80.0f)) return 1;
+    if (!l.ensure_rows({700, 333, 700, 131})) return 2;
+    if (l.ensure_rows({700, 333})) return 3;
+    for (int s : {700, 333, 131}) if (check(l, s, k, 80.0f)) return 1;
+    StatLut m; m.k = k; m.pid = 80.0f; m.ensure(130);           // second context: rows come from the process-wide cache
+    if (m.ident != std::vector<float>(l.ident.begin(), l.ident.begin() + m.ident.size()) || m.minHits != std::vector<int32_t>(l.minHits.begin(), l.minHits.begin() + 131)) return 4;
+  }
+  puts("ok");
+}
+''')
+    exe = tmp_path / "t"
+    csrc = os.path.join(ROOT, "fastani_b200", "csrc")
+    r = subprocess.run(["g++", "-O2", "-std=c++17", "-I", csrc, "-I", cuda_inc, str(src), os.path.join(csrc, "stats.cpp"), "-o", str(exe), "-lpthread"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", (r.returncode, r.stdout)
