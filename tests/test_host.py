@@ -217,7 +217,9 @@ def test_host_packer_matches_the_reference_bytes():
     seq = bytearray(rng.choice(np.frombuffer(b"ACGTacgt", np.uint8), 100003).tobytes())
     seq[5:9] = b"NNnn"; seq[40:44] = b"RYkm"; seq[16] = ord("z"); seq[31] = 0xC3; seq[32] = ord("-"); seq[100002] = ord("n")
     seq[2000:2600] = b"N" * 600
-    cases = [bytes(seq), b"", b"A", b"acgtn", bytes(seq[:16]), bytes(seq[:17]), b"N" * 33]
+    cases = [bytes(seq), b"", b"A", b"acgtn", bytes(seq[:16]), bytes(seq[:17]), b"N" * 33,
+             rng.integers(0, 256, 4099, dtype=np.uint8).tobytes(),                                  # every byte value
+             bytes(rng.choice(np.frombuffer(b"ACGTacgtBDHbdhSsUu@`[{", np.uint8), 8191).tobytes())]  # neighbours of the letters in the ASCII table
     for sq in cases:
         b = fb.PackedBatch([[("x", sq)]])
         n = len(sq)
