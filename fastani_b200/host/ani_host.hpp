@@ -12,14 +12,17 @@
 // library; without a GPU their constructors throw (the library has no CPU fallback).
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdint>
+#include <cstring>
 #include <fstream>
 #include <functional>
 #include <iostream>
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <tuple>
 #include <unordered_map>
 #include <vector>
@@ -98,34 +101,65 @@ inline void pack_genome(bani_host::HostGenome &g)
   g.packed = true;
 }
 
+// One upload batch on the host: the packed genomes [i, j) back to back in one array per kind, with the offset tables
+// bani_genome_create_packed_batch takes.  The copies are made by `threads` threads into uninitialised storage (first touch
+// of 1 GB of fresh pages by one thread costs more than parsing the files did).
+struct HostBatch {
+  std::unique_ptr<uint32_t[]> w; size_t words = 0;
+  std::vector<uint32_t> ep; std::vector<uint8_t> eb;
+  std::vector<int32_t> genOff, clen; std::vector<int64_t> woff, eoff;
+};
+
+inline HostBatch assemble_batch(const std::vector<const bani_host::HostGenome *> &gs, size_t i, size_t j, int threads)
+{
+  HostBatch b;
+  std::vector<size_t> wAt, eAt;
+  size_t wp = 0, epos = 0;
+  b.genOff.assign(1, 0); b.eoff.assign(1, 0);
+  for (size_t g = i; g < j; g++) {
+    const auto &G = *gs[g];
+    if (!G.packed) throw std::runtime_error("upload_genomes: genome " + G.path + " has not been packed");
+    wAt.push_back(wp); eAt.push_back(epos);
+    for (size_t c = 0; c < G.contigs.size(); c++) {
+      b.clen.push_back((int32_t)G.contigs[c].len); b.woff.push_back((int64_t)wp + G.wordOff[c]); b.eoff.push_back((int64_t)epos + G.excOff[c + 1]);
+    }
+    wp += G.words.size(); epos += G.excPos.size();
+    b.genOff.push_back((int32_t)b.clen.size());
+  }
+  b.clen.push_back(0); b.woff.push_back((int64_t)wp);
+  b.words = wp;
+  b.w.reset(new uint32_t[wp + 8]);
+  memset(b.w.get() + wp, 0, 8 * sizeof(uint32_t));
+  b.ep.resize(epos + 1); b.eb.resize(epos + 1);
+  const size_t n = j - i;
+  const int nt = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(threads, 1), n));
+  std::atomic<size_t> next(0);
+  auto work = [&]() {
+    for (size_t k; (k = next++) < n;) {
+      const auto &G = *gs[i + k];
+      if (!G.words.empty()) memcpy(b.w.get() + wAt[k], G.words.data(), 4 * G.words.size());
+      if (!G.excPos.empty()) { memcpy(b.ep.data() + eAt[k], G.excPos.data(), 4 * G.excPos.size()); memcpy(b.eb.data() + eAt[k], G.excByte.data(), G.excByte.size()); }
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < nt; t++) th.emplace_back(work);
+  work();
+  for (auto &t : th) t.join();
+  return b;
+}
+
 // Uploads host-packed genomes (bani_genome_create_packed_batch): the genomes of a batch are laid out back to back in one
 // host array per kind; the library copies them in groups on its copy stream.
 inline void upload_genomes(bani_ctx *ctx, const std::vector<const bani_host::HostGenome *> &gs,
-                           std::vector<std::unique_ptr<DeviceGenome>> &out, size_t batchWords = (size_t)1 << 28)
+                           std::vector<std::unique_ptr<DeviceGenome>> &out, size_t batchWords = (size_t)1 << 28, int threads = 8)
 {
   size_t i = 0;
   while (i < gs.size()) {
-    size_t j = i, words = 0, exc = 0;
-    while (j < gs.size() && (j == i || words + gs[j]->words.size() <= batchWords)) {
-      if (!gs[j]->packed) throw std::runtime_error("upload_genomes: genome " + gs[j]->path + " has not been packed");
-      words += gs[j]->words.size(); exc += gs[j]->excPos.size(); j++;
-    }
-    std::vector<uint32_t> w(words + 8, 0u), ep(exc + 1); std::vector<uint8_t> eb(exc + 1);
-    std::vector<int32_t> genOff(1, 0), clen; std::vector<int64_t> woff, eoff(1, 0);
-    size_t wp = 0, epos = 0;
-    for (size_t g = i; g < j; g++) {
-      const auto &G = *gs[g];
-      memcpy(w.data() + wp, G.words.data(), 4 * G.words.size());
-      if (!G.excPos.empty()) { memcpy(ep.data() + epos, G.excPos.data(), 4 * G.excPos.size()); memcpy(eb.data() + epos, G.excByte.data(), G.excByte.size()); }
-      for (size_t c = 0; c < G.contigs.size(); c++) {
-        clen.push_back((int32_t)G.contigs[c].len); woff.push_back((int64_t)wp + G.wordOff[c]); eoff.push_back((int64_t)epos + G.excOff[c + 1]);
-      }
-      wp += G.words.size(); epos += G.excPos.size();
-      genOff.push_back((int32_t)clen.size());
-    }
-    clen.push_back(0); woff.push_back((int64_t)wp);
+    size_t j = i, words = 0;
+    while (j < gs.size() && (j == i || words + gs[j]->words.size() <= batchWords)) { words += gs[j]->words.size(); j++; }
+    HostBatch b = assemble_batch(gs, i, j, threads);
     std::vector<bani_genome *> hs(j - i, nullptr);
-    check(bani_genome_create_packed_batch(ctx, (int32_t)(j - i), genOff.data(), clen.data(), woff.data(), w.data(), eoff.data(), ep.data(), eb.data(),
+    check(bani_genome_create_packed_batch(ctx, (int32_t)(j - i), b.genOff.data(), b.clen.data(), b.woff.data(), b.w.get(), b.eoff.data(), b.ep.data(), b.eb.data(),
                                           /*async=*/0, hs.data()), "bani_genome_create_packed_batch");
     for (size_t g = i; g < j; g++) { auto d = std::make_unique<DeviceGenome>(); d->h = hs[g - i]; d->host = gs[g]; out.push_back(std::move(d)); }
     i = j;

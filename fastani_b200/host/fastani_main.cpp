@@ -277,7 +277,7 @@ int main(int argc, char **argv)
           for (const auto &q : parameters.querySequences) qrySlot.push_back(derivable(q) ? -1 : want(q));
           std::vector<const bani_host::HostGenome *> hs; for (int id : need) hs.push_back(&genomes[id]);
           std::vector<std::unique_ptr<DeviceGenome>> dev;
-          upload_genomes(ctx, hs, dev);
+          upload_genomes(ctx, hs, dev, (size_t)1 << 28, std::max(1, parameters.threads / G));
           std::vector<std::string> shardRefNames;
           for (int j : shards[g]) shardRefNames.push_back(parameters.refSequences[j]);
 

@@ -327,3 +327,52 @@ int main() {
     assert r.returncode == 0, r.stderr
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.strip() == "ok", (r.returncode, r.stdout)
+
+
+def test_upload_batches_are_assembled_in_parallel_like_in_sequence(tmp_path):
+    """host/ani_host.hpp assemble_batch (the staging of host-packed genomes before bani_genome_create_packed_batch: copies made by
+    several threads into uninitialised storage) against the plain back-to-back layout, genomes without contigs and empty contigs included."""
+    import subprocess
+    src = tmp_path / "b.cpp"
+    src.write_text(r'''#include "ani_host.hpp"
+#include <cstdio>
+#include <random>
+int main() {
+  std::mt19937 rng(3);
+  std::vector<bani_host::HostGenome> gs(37);
+  for (auto &g : gs) {
+    const int nc = rng() % 4;                                      // also genomes without contigs
+    for (int c = 0; c < nc; c++) {
+      bani_host::Contig ct; ct.name = "c"; ct.off = g.seq.size(); ct.len = (rng() % 5 == 0) ? 0 : rng() % 3000;
+      for (uint64_t i = 0; i < ct.len; i++) g.seq.push_back("ACGTNacgtn"[rng() % ((rng() % 7 == 0) ? 10 : 4)]);
+      g.contigs.push_back(ct);
+    }
+    skch::pack_genome(g);
+  }
+  std::vector<const bani_host::HostGenome *> ps; for (auto &g : gs) ps.push_back(&g);
+  for (int threads : {1, 5}) for (auto range : {std::pair<size_t, size_t>{0, 37}, {3, 4}, {10, 30}}) {
+    skch::HostBatch b = skch::assemble_batch(ps, range.first, range.second, threads);
+    // straightforward serial statement of the same layout
+    std::vector<uint32_t> w, ep; std::vector<uint8_t> eb; std::vector<int32_t> genOff(1, 0), clen; std::vector<int64_t> woff, eoff(1, 0);
+    for (size_t g = range.first; g < range.second; g++) {
+      const auto &G = gs[g];
+      for (size_t c = 0; c < G.contigs.size(); c++) { clen.push_back((int32_t)G.contigs[c].len); woff.push_back((int64_t)w.size() + G.wordOff[c]); eoff.push_back((int64_t)ep.size() + G.excOff[c + 1]); }
+      w.insert(w.end(), G.words.begin(), G.words.end()); ep.insert(ep.end(), G.excPos.begin(), G.excPos.end()); eb.insert(eb.end(), G.excByte.begin(), G.excByte.end());
+      genOff.push_back((int32_t)clen.size());
+    }
+    clen.push_back(0); woff.push_back((int64_t)w.size());
+    bool ok = b.words == w.size() && (w.empty() || !memcmp(b.w.get(), w.data(), 4 * w.size())) && genOff == b.genOff && clen == b.clen && woff == b.woff && eoff == b.eoff;
+    for (int t = 0; t < 8; t++) ok = ok && b.w[b.words + t] == 0;
+    ok = ok && b.ep.size() == ep.size() + 1 && std::equal(ep.begin(), ep.end(), b.ep.begin()) && std::equal(eb.begin(), eb.end(), b.eb.begin());
+    if (!ok) { printf("mismatch threads %d range %zu %zu\\n", threads, range.first, range.second); return 1; }
+  }
+  puts("ok");
+}
+''')
+    exe = tmp_path / "b"
+    libdir = os.path.join(ROOT, "fastani_b200", "lib")
+    r = subprocess.run(["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "fastani_b200", "host"), "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                        "-L", libdir, "-lfastani_b200", "-lz", "-lpthread", "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", (r.returncode, r.stdout, r.stderr)
