@@ -11,12 +11,14 @@
 // GSL's gsl_cdf_binomial_Q (third party, not vendored by the reference) is replaced
 // by its definition: the upper tail of the binomial distribution.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <map>
 #include <memory>
 #include <mutex>
+#include <system_error>
 #include <thread>
 #include <tuple>
 #include <vector>
@@ -222,25 +224,24 @@ std::vector<std::shared_ptr<const LutRow>> rows_for(int k, float pid, const std:
     std::vector<std::shared_ptr<LutRow>> made(missing.size());
     unsigned hw = std::thread::hardware_concurrency();
     size_t nt = std::min<size_t>(std::min<size_t>(hw ? hw : 1, 16), missing.size());
-    // a row of size s costs ~s^2: deal the rows round-robin in decreasing size so the threads finish together
+    // a row of size s costs ~s^2: largest first, each thread takes the next row that nobody has taken
     std::vector<size_t> order(missing.size());
     for (size_t i = 0; i < order.size(); i++) order[i] = i;
     std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return want[missing[a]] > want[missing[b]]; });
-    auto work = [&](size_t t) {
+    std::atomic<size_t> next(0);
+    auto work = [&]() {
       std::vector<long double> scratch;
-      for (size_t j = t; j < order.size(); j += nt) {
+      for (size_t j; (j = next++) < order.size();) {
         auto r = std::make_shared<LutRow>();
         lut_row(k, pid, want[missing[order[j]]], scratch, *r);
         made[order[j]] = std::move(r);
       }
     };
-    if (nt <= 1) work(0);
-    else {
-      std::vector<std::thread> th;
-      for (size_t t = 1; t < nt; t++) th.emplace_back(work, t);
-      work(0);
-      for (auto &x : th) x.join();
-    }
+    std::vector<std::thread> th;
+    try { for (size_t t = 1; t < nt; t++) th.emplace_back(work); }
+    catch (const std::system_error &) {}                          // no more threads to be had: the ones that exist do the work
+    work();
+    for (auto &x : th) x.join();
     for (size_t j = 0; j < missing.size(); j++) {
       out[missing[j]] = made[j];
       g_rows[RowKey{k, pb, want[missing[j]]}] = made[j];

@@ -22,6 +22,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <system_error>
 #include <thread>
 #include <tuple>
 #include <unordered_map>
@@ -142,7 +143,8 @@ inline HostBatch assemble_batch(const std::vector<const bani_host::HostGenome *>
     }
   };
   std::vector<std::thread> th;
-  for (int t = 1; t < nt; t++) th.emplace_back(work);
+  try { for (int t = 1; t < nt; t++) th.emplace_back(work); }
+  catch (const std::system_error &) {}                            // no more threads to be had: the ones that exist do the work
   work();
   for (auto &t : th) t.join();
   return b;
